@@ -1,0 +1,1172 @@
+// IVF-Flat inner-product index on the device (K2/K3/K4 of the hot path).
+//
+// Replaces the Faiss objects used at reference src/ann_solo/spectral_library.py:167-181
+// (IndexFlatIP + IndexIVFFlat(METRIC_INNER_PRODUCT): train / add) and :443-444, :490-497
+// (nprobe, search). Faiss is a third-party library that is absent from the reference tree, so the
+// arithmetic is the one the oracle defines (oracle/solo_oracle.cpp §4):
+//   score(q, x) = fp32 sequential fmaf over dimensions 0..d-1; order = (score desc, id asc).
+//
+// Pipeline for one batch of queries:
+//   1. queries -> sparse rows (hashed spectra have <= ~50 non-zeros of 800)
+//   2. K2 coarse: exact scores against all centroids (centroid tile transposed in shared
+//      memory, lane = centroid, sequential fmaf over the query's non-zeros in index order)
+//   3. nprobe selection: block radix-select on (score, id) keys
+//   4. (query, probe) pairs inverted into per-list query groups (two rounds, see below)
+//   5. K3 list scan: every list is read once per round and scored against its query group;
+//      a score reaches HBM only if it passes the query's running threshold
+//   6. K4: k-th largest by radix select; ties broken by id; optional fused precursor-window
+//      mask (applied AFTER the top-k, reference spectral_library.py:441-446).
+// Round 0 scans each query's first probes without a threshold (bounded by C0 scores) to seed
+// tau[q] = k-th best so far; round 1 scans the rest and appends only scores >= tau[q].
+#include "ivf.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <random>
+
+namespace solo {
+
+// ======================================================================= small utilities
+
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t *__restrict__ cnt, int64_t n, int64_t *__restrict__ off, int64_t base) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = base;
+    __syncthreads();
+    for (int64_t tile = 0; tile < n; tile += 1024) {
+        int64_t i = tile + tid;
+        int64_t v = i < n ? (int64_t)max(cnt[i], 0) : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        int64_t prefix = (warp > 0 ? s_warp[warp - 1] : 0) + s_carry;
+        if (i < n) off[i] = prefix + x - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = prefix + x;
+        __syncthreads();
+    }
+    if (tid == 0) off[n] = s_carry;
+}
+
+static void scan_counts(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off, int64_t base) {
+    scan_counts_kernel<<<1, 1024, 0, h->stream>>>(cnt, n, off, base);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+void scan_counts_i32(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off) { scan_counts(h, cnt, n, off, 0); }
+
+// k-th largest (k >= 1) of `n` 32-bit keys in shared memory, restricted to entries with
+// key != skip_key when use_skip. Every thread of the block must call it. On return *count_gt
+// holds the number of participating keys strictly greater than the result.
+__device__ uint32_t block_kth_largest_u32(const uint32_t *keys, int n, int k, bool use_skip, uint32_t skip_key,
+                                          uint32_t *s_hist /*256*/, uint32_t *s_bc /*4*/, int *count_gt) {
+    uint32_t prefix = 0, mask = 0;
+    int kk = k;
+    int gt = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t key = keys[i];
+            if (use_skip && key == skip_key) continue;
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // lane L owns bins [8L, 8L+8); walk from the top bin down
+            const int lane = threadIdx.x;
+            uint32_t loc[8];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                loc[b] = s_hist[lane * 8 + b];
+                sum += loc[b];
+            }
+            // suffix sum over lanes: above = total count in lanes > lane
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_down_sync(0xffffffffu, incl, o);
+                if (lane + o < 32) incl += y;
+            }
+            uint32_t above = incl - sum;
+            bool mine = (above < (uint32_t)kk) && (incl >= (uint32_t)kk);
+            if (mine) {
+                uint32_t cum = above;
+                int digit = 0;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) {
+                    if (cum < (uint32_t)kk && cum + loc[b] >= (uint32_t)kk) {
+                        digit = lane * 8 + b;
+                        s_bc[0] = (uint32_t)digit;
+                        s_bc[1] = cum;  // participating keys with a larger digit at this level
+                    }
+                    cum += loc[b];
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t digit = s_bc[0];
+        uint32_t larger = s_bc[1];
+        gt += (int)larger;
+        kk -= (int)larger;
+        prefix |= digit << shift;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    *count_gt = gt;
+    return prefix;
+}
+
+// bitonic sort, descending, of n (power of two) 64-bit keys in shared memory
+__device__ void block_bitonic_desc_u64(unsigned long long *a, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                bool desc = ((i & size) == 0);
+                unsigned long long x = a[i], y = a[j];
+                if ((x < y) == desc) {
+                    a[i] = y;
+                    a[j] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ======================================================================= dense -> sparse rows
+
+__global__ void dense_count_kernel(const float *__restrict__ x, int64_t n, int d, int32_t *__restrict__ nnz,
+                                   uint8_t *__restrict__ bad, int32_t *__restrict__ stats, int stat_base) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *r = x + row * d;
+    int cnt = 0;
+    bool isbad = false, neg = false;
+    float ss = 0.f;
+    for (int j = lane; j < d; j += 32) {
+        float v = r[j];
+        cnt += (v != 0.f) ? 1 : 0;  // NaN != 0 counts, but the row is dropped below
+        isbad |= !isfinite(v);
+        neg |= (v < 0.f);
+        ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    isbad = __any_sync(0xffffffffu, isbad);
+    neg = __any_sync(0xffffffffu, neg);
+    if (lane == 0) {
+        nnz[row] = isbad ? 0 : cnt;
+        bad[row] = isbad ? 1 : 0;
+        if (!isbad) {
+            if (neg) atomicOr(&stats[stat_base], 1);
+            atomicMax(&stats[stat_base + 1], __float_as_int(sqrtf(ss)));
+        }
+    }
+}
+
+__global__ void dense_fill_kernel(const float *__restrict__ x, int64_t n, int d, const int64_t *__restrict__ off,
+                                  const uint8_t *__restrict__ bad, uint16_t *__restrict__ idx,
+                                  float *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    if (bad[row]) return;
+    const float *r = x + row * d;
+    int64_t o = off[row];
+    for (int base = 0; base < d; base += 32) {
+        int j = base + lane;
+        float v = j < d ? r[j] : 0.f;
+        bool nz = v != 0.f;
+        unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (nz) {
+            int pos = __popc(m & ((1u << lane) - 1u));
+            idx[o + pos] = (uint16_t)j;
+            val[o + pos] = v;
+        }
+        o += __popc(m);
+    }
+}
+
+// ======================================================================= K2: exact coarse scores
+
+constexpr int CO_WARPS = 8;
+constexpr int CO_PAD = 33;
+
+// MODE 0: scores[row * nlist + c]; MODE 1: best[row] = max over c of (score, -c) composite key
+template <int MODE>
+__global__ void __launch_bounds__(CO_WARPS * 32)
+coarse_exact_kernel(const int64_t *__restrict__ r_off, const uint16_t *__restrict__ r_idx,
+                    const float *__restrict__ r_val, int64_t row0, int64_t nrows, const float *__restrict__ cent,
+                    int nlist, int d, float *__restrict__ scores, unsigned long long *__restrict__ best) {
+    extern __shared__ float s_c[];  // [d][CO_PAD]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * 32;
+    for (int c = warp; c < 32; c += CO_WARPS) {
+        const int cc = c0 + c;
+        for (int j = lane; j < d; j += 32) s_c[j * CO_PAD + c] = cc < nlist ? cent[(int64_t)cc * d + j] : 0.f;
+    }
+    __syncthreads();
+    const int cmine = c0 + lane;
+    for (int64_t r = (int64_t)blockIdx.y * CO_WARPS + warp; r < nrows; r += (int64_t)gridDim.y * CO_WARPS) {
+        const int64_t b = r_off[row0 + r], e = r_off[row0 + r + 1];
+        float acc = 0.f;
+        for (int64_t t0 = b; t0 < e; t0 += 32) {
+            int64_t t = t0 + lane;
+            int ei = t < e ? (int)r_idx[t] : 0;
+            float ev = t < e ? r_val[t] : 0.f;
+            int cnt = (int)min((int64_t)32, e - t0);
+            for (int u = 0; u < cnt; ++u) {
+                int i = __shfl_sync(0xffffffffu, ei, u);
+                float v = __shfl_sync(0xffffffffu, ev, u);
+                acc = __fmaf_rn(v, s_c[i * CO_PAD + lane], acc);
+            }
+        }
+        if (MODE == 0) {
+            if (cmine < nlist) scores[(row0 + r) * nlist + cmine] = acc;
+        } else {
+            unsigned long long key = 0ull;
+            if (cmine < nlist && acc == acc)
+                key = ((unsigned long long)ivf_f2o(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)cmine);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long y = __shfl_xor_sync(0xffffffffu, key, o);
+                key = y > key ? y : key;
+            }
+            if (lane == 0 && key) atomicMax(&best[row0 + r], key);
+        }
+    }
+}
+
+template <int MODE>
+static void launch_coarse(solo_handle *h, const IvfIndex &ix, const int64_t *r_off, const uint16_t *r_idx,
+                          const float *r_val, int64_t row0, int64_t nrows, float *scores,
+                          unsigned long long *best) {
+    if (nrows <= 0) return;
+    auto k = coarse_exact_kernel<MODE>;
+    size_t smem = (size_t)ix.dim * CO_PAD * sizeof(float);
+    SOLO_REQUIRE(smem <= 220 * 1024, SOLO_ECAPACITY, "dim %d too large for the coarse kernel", ix.dim);
+    SOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tiles = div_up(ix.nlist, 32);
+    int per_sm = smem > 110 * 1024 ? 1 : 2;
+    int want = kNumSMs * per_sm * 4;
+    int ysplit = std::max(1, std::min(div_up(want, tiles), div_up(nrows, CO_WARPS)));
+    ysplit = std::min(ysplit, 65535);
+    dim3 grid(tiles, ysplit);
+    k<<<grid, CO_WARPS * 32, smem, h->stream>>>(r_off, r_idx, r_val, row0, nrows, ix.cent.as<float>(), ix.nlist,
+                                                ix.dim, scores, best);
+    SOLO_CUDA(cudaGetLastError());
+}
+
+__global__ void decode_assign_kernel(const unsigned long long *__restrict__ best, const uint8_t *__restrict__ bad,
+                                     int64_t n, int32_t *__restrict__ row_list) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = best[i];
+    const bool isbad = bad ? (bad[i] != 0) : (row_list[i] < 0);  // re-assignment keeps skipped rows skipped
+    row_list[i] = (isbad || k == 0ull) ? -1 : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+}
+
+// ======================================================================= probe selection
+
+constexpr int SEL_THREADS = 1024;
+
+// one CTA per query; keys = ordered score; ties at the threshold resolved towards lower list id
+__global__ void __launch_bounds__(SEL_THREADS)
+select_probes_kernel(const float *__restrict__ scores, int nlist, int nprobe, int32_t *__restrict__ probes,
+                     unsigned long long *__restrict__ probe_keys) {
+    extern __shared__ uint32_t s_keys[];  // [nlist]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_bc[4];
+    __shared__ int s_cnt, s_eq_taken;
+    const int q = blockIdx.x;
+    const float *row = scores + (int64_t)q * nlist;
+    for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
+        float s = row[i];
+        s_keys[i] = (s == s) ? ivf_f2o(s) : 0u;  // NaN -> lowest key
+    }
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_eq_taken = 0;
+    }
+    __syncthreads();
+    int gt;
+    const uint32_t T = block_kth_largest_u32(s_keys, nlist, nprobe, false, 0u, s_hist, s_bc, &gt);
+    const int need_eq = nprobe - gt;
+    // strictly greater: any order
+    for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
+        if (s_keys[i] > T) {
+            int slot = atomicAdd(&s_cnt, 1);
+            if (probes) probes[(int64_t)q * nprobe + slot] = i;
+            if (probe_keys)
+                probe_keys[(int64_t)q * nprobe + slot] =
+                    ((unsigned long long)s_keys[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+        }
+    }
+    __syncthreads();
+    // equal to the threshold: lowest ids first (ordered, chunk by chunk)
+    for (int base = 0; base < nlist; base += blockDim.x) {
+        if (s_eq_taken >= need_eq) break;  // uniform: read after the barrier below
+        int i = base + threadIdx.x;
+        bool eq = i < nlist && s_keys[i] == T;
+        unsigned m = __ballot_sync(0xffffffffu, eq);
+        __shared__ int s_wsum[SEL_THREADS / 32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = s_eq_taken;
+        for (int w = 0; w < warp; ++w) before += s_wsum[w];
+        int mypos = before + __popc(m & ((1u << lane) - 1u));
+        if (eq && mypos < need_eq) {
+            int slot = gt + mypos;
+            if (probes) probes[(int64_t)q * nprobe + slot] = i;
+            if (probe_keys)
+                probe_keys[(int64_t)q * nprobe + slot] =
+                    ((unsigned long long)T << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_wsum[w];
+            s_eq_taken += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// sort each row of n u64 keys descending (n <= 4096), decode to list ids
+__global__ void __launch_bounds__(512)
+sort_probe_rows_kernel(unsigned long long *__restrict__ keys, int n, int npad, int32_t *__restrict__ out) {
+    extern __shared__ unsigned long long s_k[];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) s_k[i] = i < n ? keys[(int64_t)q * n + i] : 0ull;
+    __syncthreads();
+    block_bitonic_desc_u64(s_k, npad);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        out[(int64_t)q * n + i] = (int32_t)(0xFFFFFFFFu - (uint32_t)(s_k[i] & 0xFFFFFFFFull));
+}
+
+// ======================================================================= grouping (two rounds)
+
+// r0[q] = number of leading probes whose lists together hold <= c0 vectors (at least one)
+__global__ void round0_split_kernel(const int32_t *__restrict__ probes, int nq, int nprobe,
+                                    const int64_t *__restrict__ list_off, int64_t c0, int32_t *__restrict__ r0) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int64_t acc = 0;
+    int r = 0;
+    for (; r < nprobe; ++r) {
+        int l = probes[(int64_t)q * nprobe + r];
+        int64_t len = list_off[l + 1] - list_off[l];
+        if (r > 0 && acc + len > c0) break;
+        acc += len;
+    }
+    r0[q] = r;
+}
+
+__global__ void group_count_kernel(const int32_t *__restrict__ probes, int nq, int nprobe,
+                                   const int32_t *__restrict__ r0, int nlist, int32_t *__restrict__ gcnt) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nq * nprobe) return;
+    int q = (int)(t / nprobe), j = (int)(t % nprobe);
+    int l = probes[t];
+    int round = j >= r0[q] ? 1 : 0;
+    atomicAdd(&gcnt[round * nlist + l], 1);
+}
+
+__global__ void group_fill_kernel(const int32_t *__restrict__ probes, int nq, int nprobe,
+                                  const int32_t *__restrict__ r0, int nlist, const int64_t *__restrict__ goff,
+                                  int32_t *__restrict__ gcur, int32_t *__restrict__ gq) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nq * nprobe) return;
+    int q = (int)(t / nprobe), j = (int)(t % nprobe);
+    int l = probes[t];
+    int round = j >= r0[q] ? 1 : 0;
+    int pos = atomicAdd(&gcur[round * nlist + l], 1);
+    gq[goff[round * nlist + l] + pos] = q;
+}
+
+// ======================================================================= K3 engine v1 (CUDA cores, exact)
+
+constexpr int EN_WARPS = 8;
+constexpr int EN_VCH = 128;    // vectors per shared-memory chunk
+constexpr int EN_ENT = 6144;   // sparse entries per chunk
+
+struct ScanArgs {
+    const int64_t *goff;   // [nlist+1] group offsets of this round
+    const int32_t *gq;     // grouped query ids
+    const int64_t *list_off;
+    const int64_t *sp_off;
+    const uint16_t *sp_idx;
+    const float *sp_val;
+    const float *q;        // (nq, d)
+    int d;
+    const float *tau;      // [nq] append threshold (score >= tau)
+    unsigned long long *buf;  // [nq][cap] (score bits << 32 | position)
+    int32_t *cnt;          // [nq]
+    int cap;
+};
+
+__global__ void __launch_bounds__(EN_WARPS * 32) scan_exact_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) unsigned char en_smem[];
+    uint2 *s_ent = reinterpret_cast<uint2 *>(en_smem);                         // [EN_ENT]
+    int *s_voff = reinterpret_cast<int *>(s_ent + EN_ENT);                     // [EN_VCH + 1]
+    float *s_q = reinterpret_cast<float *>(s_voff + EN_VCH + 4);               // [EN_WARPS][d]
+    __shared__ int s_nv;
+    const int l = blockIdx.x;
+    const int64_t g0 = a.goff[l], g1 = a.goff[l + 1];
+    const int64_t G = g1 - g0;
+    if (G == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *myq = s_q + (size_t)warp * a.d;
+    int64_t p0 = a.list_off[l];
+    const int64_t pend = a.list_off[l + 1];
+    while (p0 < pend) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int nv = 0;
+            const int64_t e0 = a.sp_off[p0];
+            while (nv < EN_VCH && p0 + nv < pend && a.sp_off[p0 + nv + 1] - e0 <= EN_ENT) ++nv;
+            s_nv = nv;
+        }
+        __syncthreads();
+        const int nv = s_nv;
+        if (nv == 0) break;  // a single row larger than the chunk: cannot happen for dim <= EN_ENT
+        const int64_t e0 = a.sp_off[p0];
+        const int nent = (int)(a.sp_off[p0 + nv] - e0);
+        for (int t = threadIdx.x; t < nent; t += blockDim.x)
+            s_ent[t] = make_uint2((unsigned)a.sp_idx[e0 + t], __float_as_uint(a.sp_val[e0 + t]));
+        for (int v = threadIdx.x; v <= nv; v += blockDim.x) s_voff[v] = (int)(a.sp_off[p0 + v] - e0);
+        __syncthreads();
+        for (int64_t g = (int64_t)blockIdx.y * EN_WARPS + warp; g < G; g += (int64_t)gridDim.y * EN_WARPS) {
+            const int q = a.gq[g0 + g];
+            const float tau = a.tau[q];
+            const float *qrow = a.q + (int64_t)q * a.d;
+            for (int j = lane; j < a.d; j += 32) myq[j] = qrow[j];
+            __syncwarp();
+            for (int vb = 0; vb < nv; vb += 32) {
+                const int v = vb + lane;
+                float acc = 0.f;
+                bool pass = false;
+                if (v < nv) {
+                    const int b = s_voff[v], e = s_voff[v + 1];
+                    for (int t = b; t < e; ++t) {
+                        uint2 en = s_ent[t];
+                        acc = __fmaf_rn(myq[en.x], __uint_as_float(en.y), acc);
+                    }
+                    pass = acc >= tau;  // NaN never passes
+                }
+                unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (m) {
+                    int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&a.cnt[q], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (pass) {
+                        int slot = base + __popc(m & ((1u << lane) - 1u));
+                        if (slot < a.cap)
+                            a.buf[(int64_t)q * a.cap + slot] =
+                                ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)(uint32_t)(p0 + v);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        p0 += nv;
+    }
+}
+
+// ======================================================================= K4: thresholds and top-k
+
+constexpr int TK_THREADS = 1024;
+
+// After round 0: tau[q] = k-th best score so far (or -inf), buffer compacted to scores >= tau - margin.
+// retry != 0: used after an overflow — recompute tau from the (full) buffer, keep only the
+// round-0 part [0, n0) that still passes, mark non-overflowed queries done (tau = +inf).
+__global__ void __launch_bounds__(TK_THREADS)
+threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt, int32_t *__restrict__ n0,
+                 float *__restrict__ tau, int cap, int k, float rel_eps, int retry) {
+    extern __shared__ uint32_t s_keys[];  // [cap]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_bc[4];
+    __shared__ int s_out;
+    const int q = blockIdx.x;
+    unsigned long long *b = buf + (int64_t)q * cap;
+    const int raw = cnt[q];
+    if (retry) {
+        if (raw <= cap) {  // this query finished cleanly in the previous attempt
+            if (threadIdx.x == 0) tau[q] = INFINITY;
+            return;
+        }
+    }
+    const int n = min(raw, cap);
+    if (n < k) {
+        if (threadIdx.x == 0) {
+            tau[q] = -INFINITY;
+            n0[q] = n;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(b[i] >> 32)));
+    if (threadIdx.x == 0) s_out = 0;
+    __syncthreads();
+    int gt;
+    const uint32_t T = block_kth_largest_u32(s_keys, n, k, false, 0u, s_hist, s_bc, &gt);
+    const float t = ivf_o2f(T);
+    const float thr = t - 2.f * rel_eps * fabsf(t) - (rel_eps > 0.f ? 2e-6f : 0.f);
+    const int limit = retry ? n0[q] : n;  // retry: only round-0 entries survive
+    // compaction through registers (each thread owns a strided subset; two-phase to stay in place)
+    unsigned long long keep[32];
+    int nk = 0;
+    for (int i = threadIdx.x, r = 0; i < limit && r < 32; i += blockDim.x, ++r) {
+        unsigned long long e = b[i];
+        if (__uint_as_float((uint32_t)(e >> 32)) >= thr) keep[nk++] = e;
+    }
+    __syncthreads();
+    int base = nk ? atomicAdd(&s_out, nk) : 0;
+    __syncthreads();
+    for (int r = 0; r < nk; ++r) b[base + r] = keep[r];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tau[q] = thr;
+        cnt[q] = s_out;
+        n0[q] = s_out;
+    }
+}
+
+struct FinalArgs {
+    const unsigned long long *buf;
+    const int32_t *cnt;
+    const int32_t *list_ids;
+    int cap;
+    int k;
+    int32_t *overflow;     // incremented when cnt > cap
+    // sorted API output
+    int64_t *I;
+    float *D;
+    // fused output
+    int32_t *sel_ids;
+    int32_t *sel_cnt;
+    // optional precursor-window mask (applied after the top-k)
+    const double *q_prec_mz;
+    const float *lib_prec_mz32;
+    const uint8_t *lib_valid;
+    int charge;
+    double tol;
+    int tol_mode;          // -1: no mask
+};
+
+__global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
+    extern __shared__ uint32_t s_keys[];  // [cap] score keys, later id keys for ties
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_bc[4];
+    __shared__ int s_nout;
+    __shared__ unsigned long long s_sorted[IVF_MAX_K];
+    const int q = blockIdx.x;
+    const unsigned long long *b = a.buf + (int64_t)q * a.cap;
+    const int raw = a.cnt[q];
+    if (raw > a.cap) {
+        if (threadIdx.x == 0) atomicAdd(a.overflow, 1);
+        return;
+    }
+    const int n = raw;
+    const int kk = min(a.k, n);
+    if (threadIdx.x == 0) s_nout = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(b[i] >> 32)));
+    __syncthreads();
+    uint32_t T = 0, Tid = 0;
+    int gt = 0;
+    if (kk > 0) {
+        T = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt);
+        const int need_eq = kk - gt;
+        // ties at the threshold: keep the need_eq lowest ids. Re-key: tie entries -> ~id + 1 (non-zero), others -> 0.
+        int n_eq_local = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) n_eq_local += (s_keys[i] == T);
+        // (count only to skip the second select when there is exactly one tie candidate per need)
+        __syncthreads();
+        __shared__ int s_neq;
+        if (threadIdx.x == 0) s_neq = 0;
+        __syncthreads();
+        if (n_eq_local) atomicAdd(&s_neq, n_eq_local);
+        __syncthreads();
+        const int neq = s_neq;
+        if (neq > need_eq) {
+            // mark: winners by score get key 0xFFFFFFFF, losers 0, ties ~id
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                uint32_t key = s_keys[i];
+                if (key > T) s_keys[i] = 0xFFFFFFFFu;
+                else if (key < T) s_keys[i] = 0u;
+                else s_keys[i] = 0xFFFFFFFEu - (uint32_t)a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)];
+            }
+            __syncthreads();
+            int gt2;
+            // k-th largest over all keys: gt winners come first, then ties by ascending id
+            Tid = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt2);
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                uint32_t key = s_keys[i];
+                s_keys[i] = key >= T ? 0xFFFFFFFFu : 0u;
+            }
+            Tid = 0xFFFFFFFFu;
+            __syncthreads();
+        }
+    }
+    // emit
+    const bool sorted_out = a.I != nullptr;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (kk > 0 && s_keys[i] >= Tid && s_keys[i] != 0u) {
+            const unsigned long long e = b[i];
+            const int id = a.list_ids[(uint32_t)(e & 0xFFFFFFFFull)];
+            if (sorted_out) {
+                int slot = atomicAdd(&s_nout, 1);
+                s_sorted[slot] = ((unsigned long long)ivf_f2o(__uint_as_float((uint32_t)(e >> 32))) << 32) |
+                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+            } else {
+                bool ok = true;
+                if (a.tol_mode >= 0) {
+                    const double qm = a.q_prec_mz[q];
+                    const double lm = (double)a.lib_prec_mz32[id];
+                    // spectral_library.py:421-427, numexpr evaluates in float64
+                    if (a.tol_mode == SOLO_TOL_DA) ok = __dmul_rn(fabs(__dsub_rn(qm, lm)), (double)a.charge) <= a.tol;
+                    else ok = __dmul_rn(__ddiv_rn(fabs(__dsub_rn(qm, lm)), lm), 1000000.0) <= a.tol;
+                    ok = ok && a.lib_valid[id];  // spectral_library.py:453
+                }
+                if (ok) {
+                    int slot = atomicAdd(&s_nout, 1);
+                    a.sel_ids[(int64_t)q * a.k + slot] = id;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!sorted_out) {
+        if (threadIdx.x == 0) a.sel_cnt[q] = s_nout;
+        return;
+    }
+    int npad = 1;
+    while (npad < kk) npad <<= 1;
+    for (int i = kk + threadIdx.x; i < npad; i += blockDim.x) s_sorted[i] = 0ull;
+    __syncthreads();
+    if (npad > 1) block_bitonic_desc_u64(s_sorted, npad);
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+        if (i < kk) {
+            unsigned long long key = s_sorted[i];
+            a.I[(int64_t)q * a.k + i] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+            if (a.D) a.D[(int64_t)q * a.k + i] = ivf_o2f((uint32_t)(key >> 32));
+        } else {
+            a.I[(int64_t)q * a.k + i] = -1;
+            if (a.D) a.D[(int64_t)q * a.k + i] = -INFINITY;
+        }
+    }
+}
+
+// ======================================================================= list-order build
+
+__global__ void gather_len_kernel(const int32_t *__restrict__ list_ids, int64_t n, const int64_t *__restrict__ row_off,
+                                  int32_t *__restrict__ len) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int r = list_ids[p];
+    len[p] = (int32_t)(row_off[r + 1] - row_off[r]);
+}
+
+// one warp per list position: copy the sparse row, write the scaled fp16 dense row
+__global__ void build_list_order_kernel(const int32_t *__restrict__ list_ids, int64_t n,
+                                        const int64_t *__restrict__ row_off, const uint16_t *__restrict__ row_idx,
+                                        const float *__restrict__ row_val, const int64_t *__restrict__ sp_off,
+                                        uint16_t *__restrict__ sp_idx, float *__restrict__ sp_val,
+                                        __half *__restrict__ vec_h, int d, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const int r = list_ids[p];
+    const int64_t b = row_off[r], e = row_off[r + 1], o = sp_off[p];
+    __half *dst = vec_h ? vec_h + p * (int64_t)d : nullptr;
+    if (dst)
+        for (int j = lane; j < d; j += 32) dst[j] = __float2half_rn(0.f);
+    __syncwarp();
+    for (int64_t t = b + lane; t < e; t += 32) {
+        uint16_t i = row_idx[t];
+        float v = row_val[t];
+        sp_idx[o + (t - b)] = i;
+        sp_val[o + (t - b)] = v;
+        if (dst) dst[i] = __float2half_rn(v * scale);
+    }
+}
+
+__global__ void f32_to_f16_scaled_kernel(const float *__restrict__ x, int64_t n, __half *__restrict__ y, float scale) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2half_rn(x[i] * scale);
+}
+
+// ======================================================================= host side
+
+void ivf_reset(IvfIndex &ix) {
+    ix.ntotal = 0;
+    ix.nstored = 0;
+    ix.nnz = 0;
+    ix.dirty = true;
+    ix.max_norm = 0.f;
+    ix.max_list_len = 0;
+    ix.h_list_off.clear();
+}
+
+void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nlist, int dim) {
+    SOLO_REQUIRE(nlist > 0 && nlist <= IVF_MAX_NLIST, SOLO_EINVAL, "nlist must be in [1, %d] (got %d)", IVF_MAX_NLIST,
+                 nlist);
+    SOLO_REQUIRE(dim > 0 && dim <= 1536, SOLO_EINVAL, "dim must be in [1, 1536] (got %d)", dim);
+    SOLO_REQUIRE(ix.ntotal == 0, SOLO_ESTATE, "centroids cannot change while the index holds vectors; reset first");
+    ix.nlist = nlist;
+    ix.dim = dim;
+    size_t nb = (size_t)nlist * dim;
+    ix.cent.ensure(nb * sizeof(float));
+    ix.cent_h.ensure(nb * sizeof(__half));
+    ix.stats.ensure(4 * sizeof(int32_t));
+    SOLO_CUDA(cudaMemcpyAsync(ix.cent.p, h_cent, nb * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    SOLO_CUDA(cudaMemsetAsync(ix.stats.p, 0, 4 * sizeof(int32_t), h->stream));
+    bool neg = false;
+    double mx = 0;
+    for (int c = 0; c < nlist; ++c) {
+        double ss = 0;
+        for (int j = 0; j < dim; ++j) {
+            float v = h_cent[(size_t)c * dim + j];
+            neg |= v < 0.f;
+            ss += (double)v * v;
+        }
+        mx = std::max(mx, std::sqrt(ss));
+    }
+    ix.cent_max_norm = (float)mx;
+    ix.nonneg = !neg;
+    f32_to_f16_scaled_kernel<<<div_up(nb, 256), 256, 0, h->stream>>>(ix.cent.as<float>(), (int64_t)nb,
+                                                                      ix.cent_h.as<__half>(), ldexpf(1.f, ix.scale_log2));
+    SOLO_CUDA(cudaGetLastError());
+    h->launches++;
+    ivf_reset(ix);
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// sparse-convert `n` dense device rows and append them to the row-ordered store; returns nothing,
+// assignment happens in ivf_add_device
+static void append_sparse_rows(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n, DevBuf &cnt, DevBuf &bad) {
+    const int d = ix.dim;
+    cnt.ensure(n * sizeof(int32_t));
+    bad.ensure(n);
+    int rows_per_block = 8;
+    dense_count_kernel<<<div_up(n, rows_per_block), rows_per_block * 32, 0, h->stream>>>(
+        d_x, n, d, cnt.as<int32_t>(), bad.as<uint8_t>(), ix.stats.as<int32_t>(), 0);
+    SOLO_CUDA(cudaGetLastError());
+    ix.row_off.ensure_keep((ix.ntotal + n + 1) * sizeof(int64_t), (ix.ntotal + 1) * sizeof(int64_t), h->stream);
+    if (ix.ntotal == 0) SOLO_CUDA(cudaMemsetAsync(ix.row_off.p, 0, sizeof(int64_t), h->stream));
+    scan_counts(h, cnt.as<int32_t>(), n, ix.row_off.as<int64_t>() + ix.ntotal, ix.nnz);
+    int64_t new_nnz = 0;
+    SOLO_CUDA(cudaMemcpyAsync(&new_nnz, ix.row_off.as<int64_t>() + ix.ntotal + n, sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, h->stream));
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    ix.row_idx.ensure_keep(new_nnz * sizeof(uint16_t) + 64, ix.nnz * sizeof(uint16_t), h->stream);
+    ix.row_val.ensure_keep(new_nnz * sizeof(float) + 64, ix.nnz * sizeof(float), h->stream);
+    dense_fill_kernel<<<div_up(n, rows_per_block), rows_per_block * 32, 0, h->stream>>>(
+        d_x, n, d, ix.row_off.as<int64_t>() + ix.ntotal, bad.as<uint8_t>(), ix.row_idx.as<uint16_t>(),
+        ix.row_val.as<float>());
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 2;
+    ix.nnz = new_nnz;
+}
+
+void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n) {
+    SOLO_REQUIRE(ix.nlist > 0, SOLO_ESTATE, "index has no centroids (train or set_centroids first)");
+    if (n <= 0) return;
+    SOLO_REQUIRE(ix.ntotal + n < (int64_t)0x7fffffff, SOLO_ECAPACITY, "more than 2^31 rows");
+    DevBuf &cnt = h->scratch[0], &bad = h->scratch[1], &best = h->scratch[2];
+    const int64_t row0 = ix.ntotal;
+    append_sparse_rows(h, ix, d_x, n, cnt, bad);
+    best.ensure((row0 + n) * sizeof(unsigned long long));
+    SOLO_CUDA(cudaMemsetAsync(best.as<unsigned long long>() + row0, 0, n * sizeof(unsigned long long), h->stream));
+    launch_coarse<1>(h, ix, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), row0, n,
+                     nullptr, best.as<unsigned long long>());
+    ix.row_list.ensure_keep((row0 + n) * sizeof(int32_t), row0 * sizeof(int32_t), h->stream);
+    decode_assign_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(best.as<unsigned long long>() + row0,
+                                                                bad.as<uint8_t>(), n, ix.row_list.as<int32_t>() + row0);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 2;
+    ix.ntotal += n;
+    ix.dirty = true;
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void ivf_finalize(solo_handle *h, IvfIndex &ix) {
+    if (!ix.dirty) return;
+    const int64_t n = ix.ntotal;
+    const int nlist = ix.nlist;
+    std::vector<int32_t> row_list(n);
+    if (n) {
+        SOLO_CUDA(cudaMemcpyAsync(row_list.data(), ix.row_list.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    // stable bucket by list: insertion order inside every list, as Faiss `add` leaves them
+    ix.h_list_off.assign(nlist + 1, 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (row_list[i] >= 0) ix.h_list_off[row_list[i] + 1]++;
+    ix.max_list_len = 0;
+    for (int l = 0; l < nlist; ++l) {
+        ix.max_list_len = std::max(ix.max_list_len, ix.h_list_off[l + 1]);
+        ix.h_list_off[l + 1] += ix.h_list_off[l];
+    }
+    const int64_t ns = ix.h_list_off[nlist];
+    std::vector<int32_t> ids(std::max<int64_t>(ns, 1));
+    {
+        std::vector<int64_t> cur(ix.h_list_off.begin(), ix.h_list_off.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            if (row_list[i] >= 0) ids[cur[row_list[i]]++] = (int32_t)i;
+    }
+    ix.nstored = ns;
+    ix.list_off.ensure((nlist + 1) * sizeof(int64_t));
+    SOLO_CUDA(cudaMemcpyAsync(ix.list_off.p, ix.h_list_off.data(), (nlist + 1) * sizeof(int64_t),
+                              cudaMemcpyHostToDevice, h->stream));
+    ix.list_ids.ensure(std::max<int64_t>(ns, 1) * sizeof(int32_t));
+    ix.sp_off.ensure((ns + 1) * sizeof(int64_t));
+    ix.sp_idx.ensure(std::max<int64_t>(ix.nnz, 1) * sizeof(uint16_t) + 64);
+    ix.sp_val.ensure(std::max<int64_t>(ix.nnz, 1) * sizeof(float) + 64);
+    ix.vec_h.ensure(std::max<int64_t>(ns, 1) * ix.dim * sizeof(__half));
+    if (ns) {
+        SOLO_CUDA(cudaMemcpyAsync(ix.list_ids.p, ids.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        DevBuf &len = h->scratch[0];
+        len.ensure(ns * sizeof(int32_t));
+        gather_len_kernel<<<div_up(ns, 256), 256, 0, h->stream>>>(ix.list_ids.as<int32_t>(), ns,
+                                                                  ix.row_off.as<int64_t>(), len.as<int32_t>());
+        SOLO_CUDA(cudaGetLastError());
+        scan_counts(h, len.as<int32_t>(), ns, ix.sp_off.as<int64_t>(), 0);
+        build_list_order_kernel<<<div_up(ns, 8), 256, 0, h->stream>>>(
+            ix.list_ids.as<int32_t>(), ns, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(),
+            ix.row_val.as<float>(), ix.sp_off.as<int64_t>(), ix.sp_idx.as<uint16_t>(), ix.sp_val.as<float>(),
+            ix.vec_h.as<__half>(), ix.dim, ldexpf(1.f, ix.scale_log2));
+        SOLO_CUDA(cudaGetLastError());
+        h->launches += 2;
+    } else {
+        SOLO_CUDA(cudaMemsetAsync(ix.sp_off.p, 0, sizeof(int64_t), h->stream));
+    }
+    int32_t st[4] = {0, 0, 0, 0};
+    SOLO_CUDA(cudaMemcpyAsync(st, ix.stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    if (st[0]) ix.nonneg = false;
+    memcpy(&ix.max_norm, &st[1], 4);
+    ix.dirty = false;
+}
+
+// ----------------------------------------------------------------------- search
+
+static void sparsify_queries(solo_handle *h, IvfIndex &ix, const float *d_q, int nq, DevBuf &q_off, DevBuf &q_idx,
+                             DevBuf &q_val) {
+    DevBuf &cnt = h->scratch[0], &bad = h->scratch[1];
+    cnt.ensure((size_t)nq * sizeof(int32_t));
+    bad.ensure(nq);
+    DevBuf &qstats = h->scratch[3];
+    qstats.ensure(4 * sizeof(int32_t));
+    SOLO_CUDA(cudaMemsetAsync(qstats.p, 0, 4 * sizeof(int32_t), h->stream));
+    dense_count_kernel<<<div_up(nq, 8), 256, 0, h->stream>>>(d_q, nq, ix.dim, cnt.as<int32_t>(), bad.as<uint8_t>(),
+                                                            qstats.as<int32_t>(), 0);
+    SOLO_CUDA(cudaGetLastError());
+    q_off.ensure((size_t)(nq + 1) * sizeof(int64_t));
+    scan_counts(h, cnt.as<int32_t>(), nq, q_off.as<int64_t>(), 0);
+    // worst case every entry is non-zero
+    q_idx.ensure((size_t)nq * ix.dim * sizeof(uint16_t) + 64);
+    q_val.ensure((size_t)nq * ix.dim * sizeof(float) + 64);
+    dense_fill_kernel<<<div_up(nq, 8), 256, 0, h->stream>>>(d_q, nq, ix.dim, q_off.as<int64_t>(), bad.as<uint8_t>(),
+                                                           q_idx.as<uint16_t>(), q_val.as<float>());
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 2;
+}
+
+__global__ void fill_f32_kernel(float *p, int64_t n, float v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
+    SOLO_REQUIRE(ix.nlist > 0, SOLO_ESTATE, "index has no centroids");
+    ivf_finalize(h, ix);
+    const int nq = a.nq, d = ix.dim, nlist = ix.nlist;
+    if (nq <= 0) return;
+    const int nprobe = std::min(a.nprobe, nlist);
+    SOLO_REQUIRE(nprobe >= 1, SOLO_EINVAL, "nprobe must be >= 1");
+    SOLO_REQUIRE(a.coarse_only || (a.k >= 1 && a.k <= IVF_MAX_K), SOLO_EINVAL, "k must be in [1, %d] (got %d)",
+                 IVF_MAX_K, a.k);
+    cudaStream_t st = h->stream;
+
+    // scratch map: 4 q_off, 5 q_idx, 6 q_val, 7 coarse scores, 8 probes, 9 probe keys, 10 r0,
+    //              11 gcnt/gcur, 12 goff, 13 gq, 14 tau, 15 cnt, 16 n0, 17 buf, 18 overflow
+    DevBuf &q_off = h->scratch[4], &q_idx = h->scratch[5], &q_val = h->scratch[6];
+    {
+        StageTimer t(h, ST_COARSE, 0);
+        sparsify_queries(h, ix, a.q, nq, q_off, q_idx, q_val);
+    }
+    DevBuf &coarse = h->scratch[7];
+    coarse.ensure((size_t)nq * nlist * sizeof(float));
+    {
+        StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
+        launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
+                         coarse.as<float>(), nullptr);
+    }
+    DevBuf &probes = h->scratch[8], &pkeys = h->scratch[9];
+    probes.ensure((size_t)nq * nprobe * sizeof(int32_t));
+    int32_t *d_probes = probes.as<int32_t>();
+    {
+        StageTimer t(h, ST_PROBE_SELECT, 1 + (a.sort_probes ? 1 : 0));
+        size_t smem = (size_t)nlist * sizeof(uint32_t);
+        SOLO_CUDA(cudaFuncSetAttribute(select_probes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned long long *d_keys = nullptr;
+        if (a.sort_probes) {
+            pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
+            d_keys = pkeys.as<unsigned long long>();
+        }
+        select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(coarse.as<float>(), nlist, nprobe,
+                                                            a.sort_probes ? nullptr : d_probes, d_keys);
+        SOLO_CUDA(cudaGetLastError());
+        if (a.sort_probes) {
+            SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
+            int npad = 1;
+            while (npad < nprobe) npad <<= 1;
+            size_t sm2 = (size_t)npad * sizeof(unsigned long long);
+            SOLO_CUDA(cudaFuncSetAttribute(sort_probe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            sort_probe_rows_kernel<<<nq, 512, sm2, st>>>(d_keys, nprobe, npad, d_probes);
+            SOLO_CUDA(cudaGetLastError());
+        }
+    }
+    if (a.probes)
+        SOLO_CUDA(cudaMemcpyAsync(a.probes, d_probes, (size_t)nq * nprobe * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (a.coarse_only) return;
+
+    // ---- per-query candidate buffers
+    const int cap = 32768;
+    const int64_t c0 = 12288;
+    SOLO_REQUIRE(ix.max_list_len <= c0, SOLO_ECAPACITY,
+                 "an inverted list holds %lld vectors; the scan buffer supports lists up to %lld (use more lists)",
+                 (long long)ix.max_list_len, (long long)c0);
+    DevBuf &r0 = h->scratch[10], &gcnt = h->scratch[11], &goff = h->scratch[12], &gq = h->scratch[13];
+    DevBuf &tau = h->scratch[14], &cnt = h->scratch[15], &n0 = h->scratch[16], &buf = h->scratch[17];
+    DevBuf &ovf = h->scratch[18];
+    r0.ensure((size_t)nq * sizeof(int32_t));
+    gcnt.ensure((size_t)4 * nlist * sizeof(int32_t));
+    goff.ensure((size_t)(2 * nlist + 2) * sizeof(int64_t));
+    gq.ensure((size_t)nq * nprobe * sizeof(int32_t));
+    tau.ensure((size_t)nq * sizeof(float));
+    cnt.ensure((size_t)nq * sizeof(int32_t));
+    n0.ensure((size_t)nq * sizeof(int32_t));
+    buf.ensure((size_t)nq * cap * sizeof(unsigned long long));
+    ovf.ensure(sizeof(int32_t) * 2);
+    const int64_t npairs = (int64_t)nq * nprobe;
+    {
+        StageTimer t(h, ST_GROUP, 5);
+        round0_split_kernel<<<div_up(nq, 128), 128, 0, st>>>(d_probes, nq, nprobe, ix.list_off.as<int64_t>(), c0,
+                                                             r0.as<int32_t>());
+        SOLO_CUDA(cudaMemsetAsync(gcnt.p, 0, (size_t)4 * nlist * sizeof(int32_t), st));
+        group_count_kernel<<<div_up(npairs, 256), 256, 0, st>>>(d_probes, nq, nprobe, r0.as<int32_t>(), nlist,
+                                                                gcnt.as<int32_t>());
+        // one scan over [round0 lists | round1 lists]: goff[r*nlist + l]
+        scan_counts_kernel<<<1, 1024, 0, st>>>(gcnt.as<int32_t>(), 2 * nlist, goff.as<int64_t>(), 0);
+        group_fill_kernel<<<div_up(npairs, 256), 256, 0, st>>>(d_probes, nq, nprobe, r0.as<int32_t>(), nlist,
+                                                               goff.as<int64_t>(), gcnt.as<int32_t>() + 2 * nlist,
+                                                               gq.as<int32_t>());
+        SOLO_CUDA(cudaGetLastError());
+    }
+    SOLO_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * sizeof(int32_t), st));
+    SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 2 * sizeof(int32_t), st));
+    fill_f32_kernel<<<div_up(nq, 256), 256, 0, st>>>(tau.as<float>(), nq, -INFINITY);
+    h->launches++;
+
+    ScanArgs sa;
+    sa.gq = gq.as<int32_t>();
+    sa.list_off = ix.list_off.as<int64_t>();
+    sa.sp_off = ix.sp_off.as<int64_t>();
+    sa.sp_idx = ix.sp_idx.as<uint16_t>();
+    sa.sp_val = ix.sp_val.as<float>();
+    sa.q = a.q;
+    sa.d = d;
+    sa.tau = tau.as<float>();
+    sa.buf = buf.as<unsigned long long>();
+    sa.cnt = cnt.as<int32_t>();
+    sa.cap = cap;
+    const size_t en_smem = (size_t)EN_ENT * sizeof(uint2) + (EN_VCH + 4) * sizeof(int) + (size_t)EN_WARPS * d * sizeof(float);
+    SOLO_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)en_smem));
+    const int ysplit = std::max(1, std::min(64, div_up(kNumSMs * 8, nlist)));
+    const size_t tk_smem = (size_t)cap * sizeof(uint32_t);
+    SOLO_CUDA(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
+    SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
+    // expected scanned vectors per query, for the flop figure of the stage
+    const double scan_units = 2.0 * d * (double)nq * ((double)ix.nstored * nprobe / nlist);
+
+    auto run_round = [&](int round) {
+        sa.goff = goff.as<int64_t>() + (size_t)round * nlist;
+        StageTimer t(h, ST_SCAN, 1, round == 0 ? scan_units : 0.0);
+        scan_exact_kernel<<<dim3(nlist, ysplit), EN_WARPS * 32, en_smem, st>>>(sa);
+        SOLO_CUDA(cudaGetLastError());
+    };
+    run_round(0);
+    {
+        StageTimer t(h, ST_TOPK, 1);
+        threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
+                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, 0.f, 0);
+        SOLO_CUDA(cudaGetLastError());
+    }
+    FinalArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.buf = buf.as<unsigned long long>();
+    fa.cnt = cnt.as<int32_t>();
+    fa.list_ids = ix.list_ids.as<int32_t>();
+    fa.cap = cap;
+    fa.k = a.k;
+    fa.overflow = ovf.as<int32_t>();
+    fa.I = a.I;
+    fa.D = a.D;
+    fa.sel_ids = a.sel_ids;
+    fa.sel_cnt = a.sel_cnt;
+    fa.tol_mode = -1;
+    if (a.I == nullptr) {
+        SOLO_REQUIRE(a.sel_ids && a.sel_cnt, SOLO_EINVAL, "no output requested");
+        fa.q_prec_mz = a.win_q_prec_mz;
+        fa.lib_prec_mz32 = a.win_lib_prec_mz32;
+        fa.lib_valid = a.win_lib_valid;
+        fa.charge = a.win_charge;
+        fa.tol = a.win_tol;
+        fa.tol_mode = a.win_tol_mode;
+    }
+    for (int attempt = 0;; ++attempt) {
+        run_round(1);
+        {
+            StageTimer t(h, ST_TOPK, 1);
+            final_topk_kernel<<<nq, TK_THREADS, tk_smem, st>>>(fa);
+            SOLO_CUDA(cudaGetLastError());
+        }
+        // A query whose candidate buffer overflowed was not finished: raise its threshold from
+        // what the buffer holds and rescan (never truncate). One 4-byte read-back per batch.
+        int32_t n_over = 0;
+        SOLO_CUDA(cudaMemcpyAsync(&n_over, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SOLO_CUDA(cudaStreamSynchronize(st));
+        if (n_over == 0) break;
+        SOLO_REQUIRE(attempt < 8, SOLO_ECAPACITY, "candidate buffer overflow persists for %d queries", n_over);
+        SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int32_t), st));
+        StageTimer t(h, ST_TOPK, 1);
+        threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
+                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, 0.f, 1);
+        SOLO_CUDA(cudaGetLastError());
+    }
+}
+
+// ----------------------------------------------------------------------- k-means (train)
+
+// one CTA per centroid: sum the sparse rows assigned to it (list order = deterministic), normalise
+__global__ void __launch_bounds__(256)
+centroid_update_kernel(const int64_t *__restrict__ list_off, const int32_t *__restrict__ list_ids,
+                       const int64_t *__restrict__ row_off, const uint16_t *__restrict__ row_idx,
+                       const float *__restrict__ row_val, int d, float *__restrict__ cent) {
+    extern __shared__ double s_acc[];  // [d]
+    __shared__ double s_red[8];
+    const int c = blockIdx.x;
+    const int64_t p0 = list_off[c], p1 = list_off[c + 1];
+    if (p0 == p1) return;  // empty cluster keeps its previous centroid
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s_acc[j] = 0.0;
+    __syncthreads();
+    for (int64_t p = p0; p < p1; ++p) {
+        const int r = list_ids[p];
+        const int64_t b = row_off[r], e = row_off[r + 1];
+        for (int64_t t = b + threadIdx.x; t < e; t += blockDim.x) s_acc[row_idx[t]] += (double)row_val[t];
+        __syncthreads();
+    }
+    double ss = 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) ss += s_acc[j] * s_acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += s_red[w];
+    const double inv = tot > 0.0 ? 1.0 / sqrt(tot) : 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) cent[(int64_t)c * d + j] = (float)(s_acc[j] * inv);
+}
+
+void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
+               uint64_t seed) {
+    SOLO_REQUIRE(n >= nlist, SOLO_EINVAL, "need at least nlist (%d) training rows, got %lld", nlist, (long long)n);
+    // initial centroids: nlist distinct finite rows, seeded
+    std::vector<int64_t> perm(n);
+    for (int64_t i = 0; i < n; ++i) perm[i] = i;
+    std::mt19937_64 rng(seed);
+    std::vector<float> cent((size_t)nlist * dim);
+    int got = 0;
+    for (int64_t i = 0; i < n && got < nlist; ++i) {
+        std::uniform_int_distribution<int64_t> dist(i, n - 1);
+        std::swap(perm[i], perm[dist(rng)]);
+        const float *r = h_x + perm[i] * dim;
+        bool ok = true;
+        for (int j = 0; j < dim && ok; ++j) ok = std::isfinite(r[j]);
+        if (ok) memcpy(cent.data() + (size_t)got++ * dim, r, dim * sizeof(float));
+    }
+    SOLO_REQUIRE(got == nlist, SOLO_EINVAL, "not enough finite training rows");
+    ivf_reset(ix);
+    ivf_set_centroids(h, ix, cent.data(), nlist, dim);
+    // rows live on the device as sparse rows for the whole training
+    DevBuf &xd = h->scratch[19];
+    const int64_t chunk = 1 << 17;
+    xd.ensure((size_t)std::min(n, chunk) * dim * sizeof(float));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        int64_t m = std::min(chunk, n - r0);
+        SOLO_CUDA(cudaMemcpyAsync(xd.p, h_x + r0 * dim, (size_t)m * dim * sizeof(float), cudaMemcpyHostToDevice,
+                                  h->stream));
+        ivf_add_device(h, ix, xd.as<float>(), m);  // sparse rows + assignment to the initial centroids
+    }
+    for (int it = 0; it < iters; ++it) {
+        ivf_finalize(h, ix);
+        centroid_update_kernel<<<nlist, 256, dim * sizeof(double), h->stream>>>(
+            ix.list_off.as<int64_t>(), ix.list_ids.as<int32_t>(), ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(),
+            ix.row_val.as<float>(), dim, ix.cent.as<float>());
+        SOLO_CUDA(cudaGetLastError());
+        h->launches++;
+        if (it + 1 < iters) {
+            // re-assign the stored sparse rows against the updated centroids
+            DevBuf &best = h->scratch[2];
+            best.ensure(n * sizeof(unsigned long long));
+            SOLO_CUDA(cudaMemsetAsync(best.p, 0, n * sizeof(unsigned long long), h->stream));
+            launch_coarse<1>(h, ix, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), 0, n,
+                             nullptr, best.as<unsigned long long>());
+            decode_assign_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(best.as<unsigned long long>(), nullptr, n,
+                                                                        ix.row_list.as<int32_t>());
+            SOLO_CUDA(cudaGetLastError());
+            h->launches += 2;
+            ix.dirty = true;
+        }
+    }
+    // training leaves only centroids behind (Faiss `train` does not add vectors)
+    std::vector<float> out((size_t)nlist * dim);
+    SOLO_CUDA(cudaMemcpyAsync(out.data(), ix.cent.p, out.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    ivf_reset(ix);
+    ivf_set_centroids(h, ix, out.data(), nlist, dim);
+}
+
+}  // namespace solo

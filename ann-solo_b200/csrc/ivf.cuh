@@ -1,0 +1,67 @@
+// IVF-Flat inner-product index: declarations shared by ivf.cu / ivf_tc.cu / solo_api.cu.
+#pragma once
+#include "solo_common.cuh"
+
+namespace solo {
+
+constexpr int IVF_MAX_K = 2048;        // top-k rows returned per query
+constexpr int IVF_MAX_NLIST = 32768;   // coarse scores of one query are selected in shared memory
+constexpr float IVF_REL_EPS = 1.25e-3f;  // bound on |approx - exact| / sum|q_d c_d| for the fp16 tensor path
+
+// composite selection key: larger is better; (score desc, id asc) is a strict total order
+__host__ __device__ __forceinline__ uint32_t ivf_f2o(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ivf_o2f(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+#endif
+}
+
+struct IvfSearchScratch;
+
+// Everything the search needs, all device pointers.
+struct IvfSearchArgs {
+    const float *q;      // (nq, dim) fp32 query vectors
+    int nq;
+    int k;
+    int nprobe;
+    // outputs (any may be null)
+    int64_t *I;          // (nq, k) sorted (score desc, id asc), -1 padded
+    float *D;            // (nq, k) exact fp32 scores, -inf padded
+    int32_t *sel_ids;    // (nq, k) unsorted selected rows, first sel_cnt[q] valid
+    int32_t *sel_cnt;    // (nq)
+    int32_t *probes;     // (nq, nprobe) selected lists (unsorted set unless sort_probes)
+    int sort_probes;
+    int coarse_only;
+    // optional precursor-window mask fused into the (unsorted) selection output; tol_mode < 0: off
+    const double *win_q_prec_mz;
+    const float *win_lib_prec_mz32;
+    const uint8_t *win_lib_valid;
+    int win_charge;
+    double win_tol;
+    int win_tol_mode;
+};
+
+// exclusive scan of n int32 counts into n+1 int64 offsets (single CTA)
+void scan_counts_i32(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off);
+void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nlist, int dim);
+void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n);  // d_x (n, dim) on device
+void ivf_finalize(solo_handle *h, IvfIndex &ix);
+void ivf_reset(IvfIndex &ix);
+void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a);
+void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
+               uint64_t seed);
+
+}  // namespace solo

@@ -1,0 +1,757 @@
+// C-ABI of libsolo_b200.so (see include/solo_b200.h for the contract and the reference
+// interfaces each entry point replaces).
+#include <algorithm>
+#include <cmath>
+
+#include "ivf.cuh"
+#include "solo_common.cuh"
+
+using namespace solo;
+
+static thread_local std::string g_create_error;
+
+static const char *kStageNames[ST_COUNT] = {"vectorize", "coarse", "probe_select", "group", "scan",
+                                            "topk",      "candidates", "score", "h2d", "d2h"};
+
+// ---------------------------------------------------------------- host helpers
+
+// MurmurHash3_x86_32 (Austin Appleby, public domain algorithm) of the decimal string of `bin`,
+// seed 42, as mmh3.hash(str(bin_idx), 42, signed=False) at reference spectrum.py:163.
+static uint32_t murmur3_decimal_host(long long bin, uint32_t seed) {
+    char buf[32];
+    int len = snprintf(buf, sizeof buf, "%lld", bin);
+    const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+    uint32_t h = seed;
+    int nblocks = len / 4;
+    for (int i = 0; i < nblocks; ++i) {
+        uint32_t k;
+        memcpy(&k, buf + 4 * i, 4);
+        k *= c1;
+        k = (k << 15) | (k >> 17);
+        k *= c2;
+        h ^= k;
+        h = (h << 13) | (h >> 19);
+        h = h * 5u + 0xe6546b64u;
+    }
+    uint32_t k = 0;
+    const unsigned char *tail = (const unsigned char *)buf + 4 * nblocks;
+    switch (len & 3) {
+        case 3: k ^= (uint32_t)tail[2] << 16; /* fallthrough */
+        case 2: k ^= (uint32_t)tail[1] << 8;  /* fallthrough */
+        case 1:
+            k ^= tail[0];
+            k *= c1;
+            k = (k << 15) | (k >> 17);
+            k *= c2;
+            h ^= k;
+    }
+    h ^= (uint32_t)len;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+static double py_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0 && ((b < 0) != (m < 0))) m += b;
+    return m;
+}
+
+template <typename F>
+static int guarded(solo_handle *h, F &&f) {
+    try {
+        if (h) SOLO_CUDA(cudaSetDevice(h->device));
+        f();
+        return SOLO_OK;
+    } catch (const Error &e) {
+        if (h) h->last_error = e.msg;
+        else g_create_error = e.msg;
+        return e.code;
+    } catch (const std::exception &e) {
+        if (h) h->last_error = e.what();
+        else g_create_error = e.what();
+        return SOLO_ECUDA;
+    }
+}
+
+static void h2d(solo_handle *h, DevBuf &b, const void *src, size_t bytes) {
+    b.ensure(std::max<size_t>(bytes, 16));
+    if (bytes) SOLO_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+}
+
+static void drain_profile(solo_handle *h) {
+    for (int s = 0; s < ST_COUNT; ++s) {
+        for (auto &pr : h->prof[s].pending) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess)
+                h->prof[s].ms += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        h->prof[s].pending.clear();
+    }
+}
+
+static LibraryStore &get_lib(solo_handle *h, int charge) {
+    auto it = h->libs.find(charge);
+    SOLO_REQUIRE(it != h->libs.end(), SOLO_ESTATE, "no library loaded for charge %d", charge);
+    return it->second;
+}
+
+static IvfIndex &get_ivf(solo_handle *h, int charge, bool must_exist) {
+    auto it = h->ivf.find(charge);
+    if (it == h->ivf.end()) {
+        SOLO_REQUIRE(!must_exist, SOLO_ESTATE, "no ANN index for charge %d", charge);
+        return h->ivf[charge];
+    }
+    return it->second;
+}
+
+// ---------------------------------------------------------------- window-only candidates (brute force)
+
+namespace solo {
+
+__device__ __forceinline__ bool window_ok(double qm, float lm32, int charge, double tol, int mode) {
+    const double lm = (double)lm32;
+    // reference spectral_library.py:421-427 (numexpr evaluates in float64)
+    if (mode == SOLO_TOL_DA) return __dmul_rn(fabs(__dsub_rn(qm, lm)), (double)charge) <= tol;
+    return __dmul_rn(__ddiv_rn(fabs(__dsub_rn(qm, lm)), lm), 1000000.0) <= tol;
+}
+
+// one CTA per query; pass 0 counts, pass 1 fills in ascending library row order
+__global__ void __launch_bounds__(256)
+window_candidates_kernel(const double *__restrict__ q_prec_mz, const float *__restrict__ lib_prec_mz32,
+                         const uint8_t *__restrict__ lib_valid, int64_t n_lib, int charge, double tol, int mode,
+                         int32_t *__restrict__ counts, const int64_t *__restrict__ off, int32_t *__restrict__ ids) {
+    __shared__ int s_wsum[8];
+    __shared__ int64_t s_run;
+    const int q = blockIdx.x;
+    const double qm = q_prec_mz[q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_lib; base += 256) {
+        const int64_t p = base + threadIdx.x;
+        bool ok = p < n_lib && lib_valid[p] && window_ok(qm, lib_prec_mz32[p], charge, tol, mode);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) before += s_wsum[w];
+            tot += s_wsum[w];
+        }
+        if (ids && ok) ids[off[q] + s_run + before + __popc(m & ((1u << lane) - 1u))] = (int32_t)p;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (!ids && threadIdx.x == 0) counts[q] = (int)s_run;
+}
+
+}  // namespace solo
+
+// ================================================================ C-ABI
+
+extern "C" {
+
+const char *solo_version(void) { return "solo_b200 0.1 (sm_100a)"; }
+
+int solo_create(int device, solo_handle **out) {
+    if (!out) return SOLO_EINVAL;
+    *out = nullptr;
+    solo_handle *h = nullptr;
+    int rc = guarded(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        SOLO_REQUIRE(e == cudaSuccess && ndev > 0, SOLO_ECUDA,
+                     "no CUDA device available (%s); libsolo_b200 has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        SOLO_REQUIRE(device >= 0 && device < ndev, SOLO_EINVAL, "device %d out of range (%d devices)", device, ndev);
+        SOLO_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SOLO_CUDA(cudaGetDeviceProperties(&prop, device));
+        SOLO_REQUIRE(prop.major == 10, SOLO_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                     device, prop.major, prop.minor);
+        h = new solo_handle();
+        h->device = device;
+        SOLO_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+    });
+    if (rc != SOLO_OK) {
+        delete h;
+        return rc;
+    }
+    rc = solo_set_vectorizer(h, 11.0, 2010.0, 0.04, 800);  // reference defaults, config.py:71-76,179-185
+    if (rc != SOLO_OK) {
+        g_create_error = h->last_error;
+        solo_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SOLO_OK;
+}
+
+void solo_destroy(solo_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain_profile(h);
+    auto rel = [](DevBuf &b) { b.release(); };
+    rel(h->lut);
+    for (auto &kv : h->libs) {
+        LibraryStore &L = kv.second;
+        rel(L.mz); rel(L.inten); rel(L.chg); rel(L.off); rel(L.prec_mz); rel(L.prec_mz32); rel(L.prec_z); rel(L.valid);
+    }
+    for (auto &kv : h->ivf) {
+        IvfIndex &x = kv.second;
+        rel(x.cent); rel(x.cent_h); rel(x.list_off); rel(x.list_ids); rel(x.vec_h); rel(x.sp_off); rel(x.sp_idx);
+        rel(x.sp_val); rel(x.row_list); rel(x.row_off); rel(x.row_idx); rel(x.row_val); rel(x.stats);
+    }
+    rel(h->q_mz); rel(h->q_mz_vec); rel(h->q_int); rel(h->q_off); rel(h->q_prec_mz);
+    for (auto &b : h->scratch) rel(b);
+    rel(h->r_best_row); rel(h->r_best_score); rel(h->r_n_pairs); rel(h->r_pairs); rel(h->r_n_cand);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+const char *solo_last_error(const solo_handle *h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int solo_set_stream(solo_handle *h, void *cuda_stream) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    });
+}
+
+int solo_synchronize(solo_handle *h) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] { SOLO_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+// ---------------------------------------------------------------- K1
+
+int solo_set_vectorizer(solo_handle *h, double min_mz, double max_mz, double bin_size, int hash_len) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(bin_size > 0 && max_mz > min_mz, SOLO_EINVAL, "bad m/z range or bin size");
+        SOLO_REQUIRE(hash_len >= 1 && hash_len <= 1536, SOLO_EINVAL, "hash_len must be in [1, 1536] (got %d)", hash_len);
+        // reference spectrum.py:123-143 get_dim
+        double start = min_mz - py_mod(min_mz, bin_size);
+        double end = max_mz + bin_size - py_mod(max_mz, bin_size);
+        int64_t n_bins = (int64_t)nearbyint((end - start) / bin_size);
+        SOLO_REQUIRE(n_bins > 0 && n_bins < (1 << 26), SOLO_EINVAL, "unreasonable number of m/z bins");
+        h->min_mz = min_mz;
+        h->max_mz = max_mz;
+        h->bin_size = bin_size;
+        h->hash_len = hash_len;
+        h->n_bins = n_bins;
+        h->min_bound = start;
+        h->h_lut.resize(n_bins + 2);
+        for (int64_t b = 0; b < n_bins + 2; ++b)
+            h->h_lut[b] = (uint16_t)(murmur3_decimal_host(b, 42u) % (uint32_t)hash_len);
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        h2d(h, h->lut, h->h_lut.data(), h->h_lut.size() * sizeof(uint16_t));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int solo_hash_slot(solo_handle *h, int64_t bin_idx, int32_t *slot) {
+    if (!h || !slot) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(bin_idx >= 0 && bin_idx < h->n_bins + 2, SOLO_EINVAL, "bin outside the device LUT");
+        uint16_t v = 0;
+        SOLO_CUDA(cudaMemcpy(&v, h->lut.as<uint16_t>() + bin_idx, sizeof v, cudaMemcpyDeviceToHost));
+        *slot = v;
+    });
+}
+
+int solo_vectorize(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity, const int64_t *offsets,
+                   int64_t n, int norm, float *out) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(n >= 0 && offsets && out, SOLO_EINVAL, "null argument");
+        if (n == 0) return;
+        const int64_t np = offsets[n];
+        SOLO_REQUIRE(offsets[0] == 0 && np >= 0, SOLO_EINVAL, "offsets must start at 0");
+        DevBuf &dmz = h->scratch[0], &din = h->scratch[1], &doff = h->scratch[2], &dout = h->scratch[3];
+        h2d(h, dmz, mz, np * (mz_is_f64 ? 8 : 4));
+        h2d(h, din, intensity, np * 4);
+        h2d(h, doff, offsets, (n + 1) * 8);
+        dout.ensure((size_t)n * h->hash_len * sizeof(float));
+        launch_vectorize(h, dmz.p, mz_is_f64, din.as<float>(), doff.as<int64_t>(), n, np, norm, dout.as<float>(),
+                         nullptr, 0);
+        SOLO_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * h->hash_len * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---------------------------------------------------------------- library store
+
+int solo_load_library(solo_handle *h, int charge, const float *mz, const float *intensity, const uint8_t *peak_charge,
+                      const int64_t *offsets, const double *prec_mz, const float *prec_mz32,
+                      const int32_t *prec_charge, const uint8_t *valid, int64_t n) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(n >= 0 && n < 0x7fffffff, SOLO_EINVAL, "bad library size");
+        SOLO_REQUIRE(offsets && prec_mz && prec_charge, SOLO_EINVAL, "null argument");
+        SOLO_REQUIRE(offsets[0] == 0, SOLO_EINVAL, "offsets must start at 0");
+        const int64_t np = offsets[n];
+        int maxp = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t len = offsets[i + 1] - offsets[i];
+            SOLO_REQUIRE(len >= 0, SOLO_EINVAL, "offsets must be non-decreasing (row %lld)", (long long)i);
+            maxp = std::max<int64_t>(maxp, len);
+            SOLO_REQUIRE(prec_charge[i] >= 0 && prec_charge[i] <= 7, SOLO_ECAPACITY,
+                         "library row %lld has precursor charge %d; the scorer supports charges 0..7", (long long)i,
+                         prec_charge[i]);
+            // the scorer's merge (SpectrumMatch.cpp:39-55) relies on ascending m/z
+            for (int64_t p = offsets[i] + 1; p < offsets[i + 1]; ++p)
+                SOLO_REQUIRE(mz[p] >= mz[p - 1], SOLO_EINVAL, "library row %lld: m/z not ascending", (long long)i);
+        }
+        SOLO_REQUIRE(maxp <= 128, SOLO_ECAPACITY, "library spectra may hold at most 128 peaks (got %d)", maxp);
+        LibraryStore &L = h->libs[charge];
+        L.n = n;
+        L.n_peaks = np;
+        L.max_peaks = maxp;
+        h2d(h, L.mz, mz, np * 4);
+        h2d(h, L.inten, intensity, np * 4);
+        if (peak_charge) h2d(h, L.chg, peak_charge, np);
+        else {
+            L.chg.ensure(std::max<int64_t>(np, 16));
+            SOLO_CUDA(cudaMemsetAsync(L.chg.p, 0, std::max<int64_t>(np, 16), h->stream));
+        }
+        h2d(h, L.off, offsets, (n + 1) * 8);
+        h2d(h, L.prec_mz, prec_mz, n * 8);
+        std::vector<float> tmp32;
+        if (!prec_mz32) {  // reader.py:188-189 np.asarray(..., np.float32)
+            tmp32.resize(n);
+            for (int64_t i = 0; i < n; ++i) tmp32[i] = (float)prec_mz[i];
+            prec_mz32 = tmp32.data();
+        }
+        h2d(h, L.prec_mz32, prec_mz32, n * 4);
+        h2d(h, L.prec_z, prec_charge, n * 4);
+        if (valid) h2d(h, L.valid, valid, n);
+        else {
+            L.valid.ensure(std::max<int64_t>(n, 16));
+            SOLO_CUDA(cudaMemsetAsync(L.valid.p, 1, std::max<int64_t>(n, 16), h->stream));
+        }
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---------------------------------------------------------------- IVF
+
+int solo_ivf_set_centroids(solo_handle *h, int charge, const float *centroids, int nlist, int dim) {
+    if (!h || !centroids) return SOLO_EINVAL;
+    return guarded(h, [&] { ivf_set_centroids(h, get_ivf(h, charge, false), centroids, nlist, dim); });
+}
+
+int solo_ivf_train(solo_handle *h, int charge, const float *x, int64_t n, int dim, int nlist, int iters, uint64_t seed) {
+    if (!h || !x) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(nlist > 0 && nlist <= IVF_MAX_NLIST, SOLO_EINVAL, "nlist must be in [1, %d]", IVF_MAX_NLIST);
+        ivf_train(h, get_ivf(h, charge, false), x, n, dim, nlist, std::max(iters, 0), seed);
+    });
+}
+
+int solo_ivf_get_centroids(solo_handle *h, int charge, float *centroids) {
+    if (!h || !centroids) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_CUDA(cudaMemcpyAsync(centroids, ix.cent.p, (size_t)ix.nlist * ix.dim * sizeof(float), cudaMemcpyDeviceToHost,
+                                  h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int solo_ivf_add(solo_handle *h, int charge, const float *x, int64_t n, int dim) {
+    if (!h || (!x && n > 0)) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(dim == ix.dim, SOLO_EINVAL, "dim %d does not match the index (%d)", dim, ix.dim);
+        DevBuf &xd = h->scratch[19];
+        const int64_t chunk = 1 << 17;
+        xd.ensure((size_t)std::min<int64_t>(std::max<int64_t>(n, 1), chunk) * dim * sizeof(float));
+        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+            int64_t m = std::min(chunk, n - r0);
+            SOLO_CUDA(cudaMemcpyAsync(xd.p, x + r0 * dim, (size_t)m * dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            ivf_add_device(h, ix, xd.as<float>(), m);
+        }
+    });
+}
+
+int solo_ivf_add_library(solo_handle *h, int charge) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        LibraryStore &L = get_lib(h, charge);
+        SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
+        DevBuf &xd = h->scratch[19], &coff = h->scratch[20];
+        const int64_t chunk = 1 << 17;
+        xd.ensure((size_t)std::min<int64_t>(std::max<int64_t>(L.n, 1), chunk) * ix.dim * sizeof(float));
+        std::vector<int64_t> hoff(L.n + 1);
+        SOLO_CUDA(cudaMemcpy(hoff.data(), L.off.p, (L.n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        for (int64_t r0 = 0; r0 < L.n; r0 += chunk) {
+            int64_t m = std::min(chunk, L.n - r0);
+            // K1 takes offsets relative to the arrays it is handed: the store's offsets are absolute,
+            // so hand it the full arrays and the slice of offsets.
+            int64_t npk = hoff[r0 + m] - hoff[r0];
+            launch_vectorize(h, L.mz.p, 0, L.inten.as<float>(), L.off.as<int64_t>() + r0, m, npk, 1, xd.as<float>(),
+                             nullptr, 0);
+            ivf_add_device(h, ix, xd.as<float>(), m);
+        }
+        (void)coff;
+    });
+}
+
+int solo_ivf_reset(solo_handle *h, int charge) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] { ivf_reset(get_ivf(h, charge, true)); });
+}
+
+int solo_ivf_ntotal(solo_handle *h, int charge, int64_t *ntotal, int32_t *nlist, int32_t *dim) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        if (ntotal) *ntotal = ix.ntotal;
+        if (nlist) *nlist = ix.nlist;
+        if (dim) *dim = ix.dim;
+    });
+}
+
+int solo_ivf_get_assignment(solo_handle *h, int charge, int32_t *list_of_row) {
+    if (!h || !list_of_row) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        if (ix.ntotal == 0) return;
+        SOLO_CUDA(cudaMemcpyAsync(list_of_row, ix.row_list.p, ix.ntotal * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int solo_ivf_search(solo_handle *h, int charge, const float *queries, int nq, int dim, int k, int nprobe, int64_t *I,
+                    float *D) {
+    if (!h || !queries || !I) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(dim == ix.dim, SOLO_EINVAL, "dim %d does not match the index (%d)", dim, ix.dim);
+        SOLO_REQUIRE(nq >= 0, SOLO_EINVAL, "nq < 0");
+        if (nq == 0) return;
+        DevBuf &dq = h->scratch[19], &dI = h->scratch[20], &dD = h->scratch[21];
+        h2d(h, dq, queries, (size_t)nq * dim * sizeof(float));
+        dI.ensure((size_t)nq * k * sizeof(int64_t));
+        dD.ensure((size_t)nq * k * sizeof(float));
+        IvfSearchArgs a;
+        memset(&a, 0, sizeof a);
+        a.q = dq.as<float>();
+        a.nq = nq;
+        a.k = k;
+        a.nprobe = nprobe;
+        a.I = dI.as<int64_t>();
+        a.D = dD.as<float>();
+        a.win_tol_mode = -1;
+        ivf_search(h, ix, a);
+        SOLO_CUDA(cudaMemcpyAsync(I, dI.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        if (D) SOLO_CUDA(cudaMemcpyAsync(D, dD.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int solo_ivf_coarse(solo_handle *h, int charge, const float *queries, int nq, int dim, int nprobe, int32_t *probes) {
+    if (!h || !queries || !probes) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(dim == ix.dim, SOLO_EINVAL, "dim %d does not match the index (%d)", dim, ix.dim);
+        if (nq <= 0) return;
+        const int np = std::min(nprobe, ix.nlist);
+        DevBuf &dq = h->scratch[19], &dP = h->scratch[20];
+        h2d(h, dq, queries, (size_t)nq * dim * sizeof(float));
+        dP.ensure((size_t)nq * np * sizeof(int32_t));
+        IvfSearchArgs a;
+        memset(&a, 0, sizeof a);
+        a.q = dq.as<float>();
+        a.nq = nq;
+        a.k = 1;
+        a.nprobe = nprobe;
+        a.probes = dP.as<int32_t>();
+        a.sort_probes = 1;
+        a.coarse_only = 1;
+        a.win_tol_mode = -1;
+        ivf_search(h, ix, a);
+        SOLO_CUDA(cudaMemcpyAsync(probes, dP.p, (size_t)nq * np * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---------------------------------------------------------------- K5 standalone
+
+static void stage_queries_impl(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_int,
+                               const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
+    SOLO_REQUIRE(nq >= 0 && q_off && (nq == 0 || (q_mz && q_int && q_prec_mz)), SOLO_EINVAL, "null argument");
+    SOLO_REQUIRE(q_off[0] == 0, SOLO_EINVAL, "query offsets must start at 0");
+    const int64_t np = q_off[nq];
+    int maxp = 0;
+    for (int i = 0; i < nq; ++i) {
+        int64_t len = q_off[i + 1] - q_off[i];
+        SOLO_REQUIRE(len >= 0, SOLO_EINVAL, "query offsets must be non-decreasing");
+        maxp = std::max<int64_t>(maxp, len);
+        // the scorer's monotone advance (SpectrumMatch.cpp:39-46) assumes ascending query m/z
+        for (int64_t p = q_off[i] + 1; p < q_off[i + 1]; ++p)
+            SOLO_REQUIRE(q_mz[p] >= q_mz[p - 1], SOLO_EINVAL, "query %d: m/z not ascending", i);
+    }
+    SOLO_REQUIRE(maxp <= 128, SOLO_ECAPACITY, "query spectra may hold at most 128 peaks (got %d)", maxp);
+    StageTimer t(h, ST_H2D, 0, (double)(np * (8 + (q_mz_vec ? (mz_is_f64 ? 8 : 4) : 0)) + (nq + 1) * 8 + nq * 8));
+    h->nq = nq;
+    h->q_peaks = np;
+    h->q_max_peaks = maxp;
+    h->q_mz_is_f64 = mz_is_f64;
+    h2d(h, h->q_mz, q_mz, np * 4);
+    h2d(h, h->q_int, q_int, np * 4);
+    h2d(h, h->q_off, q_off, (size_t)(nq + 1) * 8);
+    h2d(h, h->q_prec_mz, q_prec_mz, (size_t)nq * 8);
+    if (q_mz_vec && (mz_is_f64 || q_mz_vec != (const void *)q_mz)) h2d(h, h->q_mz_vec, q_mz_vec, np * (mz_is_f64 ? 8 : 4));
+    else h->q_mz_is_f64 = -1;  // binning reads the float32 scorer array
+}
+
+static void ensure_results(solo_handle *h, int nq, int max_pairs) {
+    h->r_best_row.ensure(std::max(nq, 1) * sizeof(int32_t));
+    h->r_best_score.ensure(std::max(nq, 1) * sizeof(double));
+    h->r_n_pairs.ensure(std::max(nq, 1) * sizeof(int32_t));
+    h->r_n_cand.ensure(std::max(nq, 1) * sizeof(int32_t));
+    h->r_pairs.ensure((size_t)std::max(nq, 1) * max_pairs * 2 * sizeof(uint32_t));
+    h->r_nq = nq;
+    h->r_max_pairs = max_pairs;
+}
+
+int solo_best_match_batch(solo_handle *h, int charge, const float *q_mz, const float *q_intensity, const int64_t *q_off,
+                          const double *q_prec_mz, int nq, const int32_t *cand_ids, const int64_t *cand_off,
+                          double fragment_mz_tolerance, int allow_shift, int max_pairs, int32_t *best_pos,
+                          double *best_score, int32_t *n_pairs, uint32_t *pairs) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        LibraryStore &L = get_lib(h, charge);
+        SOLO_REQUIRE(cand_off && best_pos && best_score && n_pairs && pairs && max_pairs > 0, SOLO_EINVAL, "null argument");
+        if (nq == 0) return;
+        stage_queries_impl(h, q_mz, nullptr, q_intensity, q_off, q_prec_mz, nq, 0);
+        const int64_t nc = cand_off[nq];
+        for (int64_t i = 0; i < nc; ++i)
+            SOLO_REQUIRE(cand_ids[i] >= 0 && cand_ids[i] < L.n, SOLO_EINVAL, "candidate id %d out of range", cand_ids[i]);
+        DevBuf &dci = h->scratch[0], &dco = h->scratch[1], &dpos = h->scratch[2], &ovf = h->scratch[3];
+        h2d(h, dci, cand_ids, nc * sizeof(int32_t));
+        h2d(h, dco, cand_off, (size_t)(nq + 1) * sizeof(int64_t));
+        dpos.ensure((size_t)nq * sizeof(int32_t));
+        ovf.ensure(16);
+        SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
+        ensure_results(h, nq, max_pairs);
+        ScoreArgs a;
+        a.q_mz = h->q_mz.as<float>();
+        a.q_int = h->q_int.as<float>();
+        a.q_off = h->q_off.as<int64_t>();
+        a.q_prec_mz = h->q_prec_mz.as<double>();
+        a.nq = nq;
+        a.q_max_peaks = h->q_max_peaks;
+        a.lib = &L;
+        a.cand_ids = dci.as<int32_t>();
+        a.cand_off = dco.as<int64_t>();
+        a.tol = fragment_mz_tolerance;
+        a.allow_shift = allow_shift;
+        a.max_pairs = max_pairs;
+        a.best_pos = dpos.as<int32_t>();
+        a.best_row = nullptr;
+        a.best_score = h->r_best_score.as<double>();
+        a.n_pairs = h->r_n_pairs.as<int32_t>();
+        a.pairs = h->r_pairs.as<uint32_t>();
+        a.overflow = ovf.as<int32_t>();
+        launch_best_match(h, a);
+        int32_t n_over = 0;
+        SOLO_CUDA(cudaMemcpyAsync(best_pos, dpos.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaMemcpyAsync(best_score, h->r_best_score.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaMemcpyAsync(n_pairs, h->r_n_pairs.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaMemcpyAsync(pairs, h->r_pairs.p, (size_t)nq * max_pairs * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaMemcpyAsync(&n_over, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        SOLO_REQUIRE(n_over == 0, SOLO_ECAPACITY,
+                     "%d (query, candidate) pairs produced more than 256 tentative peak matches", n_over);
+    });
+}
+
+// ---------------------------------------------------------------- fused open search
+
+int solo_stage_queries(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
+                       const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] { stage_queries_impl(h, q_mz, q_mz_vec ? q_mz_vec : q_mz, q_intensity, q_off, q_prec_mz, nq, mz_is_f64); });
+}
+
+int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p) {
+    if (!h || !p) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        LibraryStore &L = get_lib(h, charge);
+        const int nq = h->nq;
+        SOLO_REQUIRE(p->tol_mode == SOLO_TOL_DA || p->tol_mode == SOLO_TOL_PPM, SOLO_EINVAL,
+                     "Unknown precursor tolerance mode");  // spectral_library.py:429
+        SOLO_REQUIRE(p->max_pairs > 0, SOLO_EINVAL, "max_pairs must be positive");
+        ensure_results(h, nq, p->max_pairs);
+        if (nq == 0) return;
+        DevBuf &ovf = h->scratch[22];
+        ovf.ensure(16);
+        SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
+        ScoreArgs a;
+        a.q_mz = h->q_mz.as<float>();
+        a.q_int = h->q_int.as<float>();
+        a.q_off = h->q_off.as<int64_t>();
+        a.q_prec_mz = h->q_prec_mz.as<double>();
+        a.nq = nq;
+        a.q_max_peaks = h->q_max_peaks;
+        a.lib = &L;
+        a.tol = p->fragment_mz_tolerance;
+        a.allow_shift = p->allow_shift;
+        a.max_pairs = p->max_pairs;
+        DevBuf &dpos = h->scratch[23];
+        dpos.ensure((size_t)nq * sizeof(int32_t));
+        a.best_pos = dpos.as<int32_t>();
+        a.best_row = h->r_best_row.as<int32_t>();
+        a.best_score = h->r_best_score.as<double>();
+        a.n_pairs = h->r_n_pairs.as<int32_t>();
+        a.pairs = h->r_pairs.as<uint32_t>();
+        a.overflow = ovf.as<int32_t>();
+        a.tie_by_row = 1;
+        const bool ann = p->use_ann && h->ivf.count(charge) && h->ivf[charge].nlist > 0;
+        if (ann) {
+            IvfIndex &ix = h->ivf[charge];
+            SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
+            SOLO_REQUIRE(p->k >= 1 && p->k <= IVF_MAX_K, SOLO_EINVAL, "num_candidates must be in [1, %d]", IVF_MAX_K);
+            // K1: query vectors
+            DevBuf &qv = h->scratch[19], &sel = h->scratch[20];
+            qv.ensure((size_t)nq * h->hash_len * sizeof(float));
+            const void *mzv = h->q_mz_is_f64 < 0 ? h->q_mz.p : h->q_mz_vec.p;
+            launch_vectorize(h, mzv, h->q_mz_is_f64 > 0 ? 1 : 0, h->q_int.as<float>(), h->q_off.as<int64_t>(), nq,
+                             h->q_peaks, 1, qv.as<float>(), nullptr, 0);
+            sel.ensure((size_t)nq * p->k * sizeof(int32_t));
+            IvfSearchArgs s;
+            memset(&s, 0, sizeof s);
+            s.q = qv.as<float>();
+            s.nq = nq;
+            s.k = p->k;
+            s.nprobe = p->nprobe;
+            s.sel_ids = sel.as<int32_t>();
+            s.sel_cnt = h->r_n_cand.as<int32_t>();
+            s.win_q_prec_mz = h->q_prec_mz.as<double>();
+            s.win_lib_prec_mz32 = L.prec_mz32.as<float>();
+            s.win_lib_valid = L.valid.as<uint8_t>();
+            s.win_charge = charge;
+            s.win_tol = p->tol_value;
+            s.win_tol_mode = p->tol_mode;
+            ivf_search(h, ix, s);
+            a.cand_ids = sel.as<int32_t>();
+            a.cand_off = nullptr;
+            a.cand_cnt = h->r_n_cand.as<int32_t>();
+            a.cand_stride = p->k;
+        } else {
+            // brute force: every valid library row inside the precursor window
+            DevBuf &coff = h->scratch[20], &cids = h->scratch[21];
+            coff.ensure((size_t)(nq + 1) * sizeof(int64_t));
+            int64_t total = 0;
+            {
+                StageTimer t(h, ST_CANDIDATES, 3);
+                window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
+                                                                    L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
+                                                                    p->tol_mode, h->r_n_cand.as<int32_t>(), nullptr, nullptr);
+                SOLO_CUDA(cudaGetLastError());
+                // offsets = exclusive scan of the counts (single-CTA scan kernel lives in ivf.cu)
+                scan_counts_i32(h, h->r_n_cand.as<int32_t>(), nq, coff.as<int64_t>());
+                SOLO_CUDA(cudaMemcpyAsync(&total, coff.as<int64_t>() + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+                SOLO_CUDA(cudaStreamSynchronize(h->stream));
+                cids.ensure(std::max<int64_t>(total, 1) * sizeof(int32_t));
+                window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
+                                                                    L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
+                                                                    p->tol_mode, nullptr, coff.as<int64_t>(), cids.as<int32_t>());
+                SOLO_CUDA(cudaGetLastError());
+            }
+            a.cand_ids = cids.as<int32_t>();
+            a.cand_off = coff.as<int64_t>();
+        }
+        launch_best_match(h, a);
+    });
+}
+
+int solo_fetch_results(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs,
+                       int32_t *n_cand) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        const int nq = h->r_nq;
+        if (nq == 0) return;
+        int32_t n_over = 0;
+        {
+            StageTimer t(h, ST_D2H, 0, (double)nq * (4 + 8 + 4 + 4 + (double)h->r_max_pairs * 8));
+            auto cp = [&](void *dst, const DevBuf &src, size_t bytes) {
+                if (dst) SOLO_CUDA(cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+            };
+            cp(best_row, h->r_best_row, (size_t)nq * 4);
+            cp(best_score, h->r_best_score, (size_t)nq * 8);
+            cp(n_pairs, h->r_n_pairs, (size_t)nq * 4);
+            cp(pairs, h->r_pairs, (size_t)nq * h->r_max_pairs * 8);
+            cp(n_cand, h->r_n_cand, (size_t)nq * 4);
+            cp(&n_over, h->scratch[22], 4);
+        }
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        SOLO_REQUIRE(n_over == 0, SOLO_ECAPACITY,
+                     "%d (query, candidate) pairs produced more than 256 tentative peak matches", n_over);
+    });
+}
+
+int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, const float *q_mz, const void *q_mz_vec,
+                      const float *q_intensity, const int64_t *q_off, const double *q_prec_mz, int nq,
+                      int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand) {
+    int rc = solo_stage_queries(h, q_mz, q_mz_vec, q_intensity, q_off, q_prec_mz, nq, p ? p->mz_is_f64 : 0);
+    if (rc) return rc;
+    rc = solo_search_staged(h, charge, p);
+    if (rc) return rc;
+    return solo_fetch_results(h, best_row, best_score, n_pairs, pairs, n_cand);
+}
+
+// ---------------------------------------------------------------- instrumentation
+
+int solo_profile_enable(solo_handle *h, int on) {
+    if (!h) return SOLO_EINVAL;
+    h->profile = on != 0;
+    return SOLO_OK;
+}
+
+int solo_profile_reset(solo_handle *h) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        drain_profile(h);
+        for (int s = 0; s < ST_COUNT; ++s) {
+            h->prof[s].ms = 0;
+            h->prof[s].launches = 0;
+            h->prof[s].units = 0;
+        }
+        h->launches = 0;
+    });
+}
+
+int solo_profile_num_stages(void) { return ST_COUNT; }
+const char *solo_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? kStageNames[stage] : ""; }
+
+int solo_profile_get(solo_handle *h, int stage, double *ms_total, int64_t *launches, double *units) {
+    if (!h || stage < 0 || stage >= ST_COUNT) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        drain_profile(h);
+        if (ms_total) *ms_total = h->prof[stage].ms;
+        if (launches) *launches = h->prof[stage].launches;
+        if (units) *units = h->prof[stage].units;
+    });
+}
+
+int64_t solo_kernel_launches(const solo_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Shared host/device declarations for libsolo_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/solo_b200.h"
+
+namespace solo {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------- errors
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define SOLO_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            char _b[512];                                                                       \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                     __FILE__, __LINE__);                                                       \
+            throw ::solo::Error{_e == cudaErrorMemoryAllocation ? SOLO_ENOMEM : SOLO_ECUDA, _b}; \
+        }                                                                                       \
+    } while (0)
+
+#define SOLO_REQUIRE(cond, code, ...)              \
+    do {                                           \
+        if (!(cond)) {                             \
+            char _b[512];                          \
+            snprintf(_b, sizeof _b, __VA_ARGS__);  \
+            throw ::solo::Error{code, _b};         \
+        }                                          \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffers
+// Grow-only device allocation owned by the handle.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            char b[256];
+            snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            throw Error{SOLO_ENOMEM, b};
+        }
+        cap = want;
+    }
+    // grow while keeping the first `keep` bytes (device-to-device copy on `stream`)
+    void ensure_keep(size_t bytes, size_t keep, cudaStream_t stream) {
+        if (bytes <= cap) return;
+        void *old = p;
+        size_t want = bytes + bytes / 2 + 256;
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) {
+            char b[256];
+            snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            throw Error{SOLO_ENOMEM, b};
+        }
+        if (old && keep) {
+            cudaMemcpyAsync(np, old, keep, cudaMemcpyDeviceToDevice, stream);
+            cudaStreamSynchronize(stream);
+        }
+        if (old) cudaFree(old);
+        p = np;
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// ---------------------------------------------------------------- profiling stages
+enum Stage {
+    ST_VECTORIZE = 0,  // K1
+    ST_COARSE,         // K2 coarse scoring
+    ST_PROBE_SELECT,   // K2 nprobe selection
+    ST_GROUP,          // invert (query, probe) -> per-list query groups
+    ST_SCAN,           // K3 list scan (dominant kernel)
+    ST_TOPK,           // K4 threshold / band re-rank / top-k
+    ST_CANDIDATES,     // window mask + compaction
+    ST_SCORE,          // K5 shifted dot
+    ST_H2D,
+    ST_D2H,
+    ST_COUNT
+};
+
+struct StageProf {
+    double ms = 0.0;
+    int64_t launches = 0;
+    double units = 0.0;  // stage-specific unit count (bytes or flops), summed
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+// ---------------------------------------------------------------- library peak store
+struct LibraryStore {
+    int64_t n = 0;
+    int64_t n_peaks = 0;
+    int max_peaks = 0;
+    DevBuf mz, inten, chg, off, prec_mz, prec_mz32, prec_z, valid;
+};
+
+// ---------------------------------------------------------------- IVF index
+struct IvfIndex {
+    int dim = 0;
+    int nlist = 0;
+    int64_t ntotal = 0;     // rows offered to add() so far (ids run 0..ntotal-1)
+    int64_t nstored = 0;    // rows actually stored (NaN rows are skipped)
+    bool nonneg = true;     // every stored value and centroid value is >= 0
+    float max_norm = 0.f;   // max L2 norm over stored rows
+    float cent_max_norm = 0.f;
+    int scale_log2 = 10;    // fp16 copies hold x * 2^scale_log2
+    // centroids
+    DevBuf cent;            // (nlist, dim) fp32 row-major
+    DevBuf cent_h;          // (nlist, dim) fp16 scaled
+    // inverted lists (rebuilt on add): positions are list-ordered
+    DevBuf list_off;        // int64 [nlist+1]
+    DevBuf list_ids;        // int32 [nstored] library row of position p
+    DevBuf vec_h;           // (nstored, dim) fp16 scaled, list order
+    DevBuf sp_off;          // int64 [nstored+1] sparse row offsets, list order
+    DevBuf sp_idx;          // uint16 [nnz]
+    DevBuf sp_val;          // float  [nnz]
+    DevBuf row_list;        // int32 [ntotal] list of row (-1 = skipped)
+    std::vector<int64_t> h_list_off;  // host copy
+    // every row ever added, in insertion order, as sparse rows (lists are rebuilt from these)
+    DevBuf row_off;         // int64 [ntotal+1]
+    DevBuf row_idx;         // uint16 [nnz]
+    DevBuf row_val;         // float  [nnz]
+    DevBuf stats;           // int32 [4]: {any_negative, max_norm_bits, cent_any_negative, cent_max_norm_bits}
+    int64_t nnz = 0;
+    bool dirty = true;      // lists need rebuilding before the next search
+    int64_t max_list_len = 0;
+    int buf_cap = 0;        // per-query candidate buffer capacity used by the scan
+};
+
+}  // namespace solo
+
+struct solo_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+    bool profile = false;
+    solo::StageProf prof[solo::ST_COUNT];
+
+    // vectoriser
+    double min_mz = 11.0, max_mz = 2010.0, bin_size = 0.04;
+    int hash_len = 800;
+    int64_t n_bins = 0;
+    double min_bound = 0.0;
+    solo::DevBuf lut;  // uint16 [n_bins + 2]
+    std::vector<uint16_t> h_lut;
+
+    std::map<int, solo::LibraryStore> libs;
+    std::map<int, solo::IvfIndex> ivf;
+
+    // staged query batch
+    int nq = 0;
+    int64_t q_peaks = 0;
+    int q_max_peaks = 0;
+    int q_mz_is_f64 = 0;
+    solo::DevBuf q_mz, q_mz_vec, q_int, q_off, q_prec_mz;
+
+    // scratch
+    solo::DevBuf scratch[24];
+    // results of the last staged search
+    solo::DevBuf r_best_row, r_best_score, r_n_pairs, r_pairs, r_n_cand;
+    int r_nq = 0, r_max_pairs = 0;
+};
+
+namespace solo {
+
+// RAII stage timer: records CUDA events around a stage when profiling is enabled.
+struct StageTimer {
+    solo_handle *h;
+    int st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(solo_handle *h_, int st_, int64_t launches, double units = 0.0) : h(h_), st(st_) {
+        h->launches += launches;
+        h->prof[st].launches += launches;
+        h->prof[st].units += units;
+        if (h->profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~StageTimer() {
+        if (a) {
+            cudaEventRecord(b, h->stream);
+            h->prof[st].pending.emplace_back(a, b);
+        }
+    }
+};
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// kernels' host launchers (defined in the .cu files)
+void launch_vectorize(solo_handle *h, const void *d_mz, int mz_is_f64, const float *d_int, const int64_t *d_off,
+                      int64_t n, int64_t n_peaks, int norm, float *d_out, __half *d_out_h, int scale_log2);
+
+struct ScoreArgs {
+    const float *q_mz;
+    const float *q_int;
+    const int64_t *q_off;
+    const double *q_prec_mz;
+    int nq;
+    int q_max_peaks;
+    const LibraryStore *lib;
+    const int32_t *cand_ids;
+    const int64_t *cand_off;   // CSR, or null with (cand_stride, cand_cnt)
+    const int32_t *cand_cnt = nullptr;
+    int cand_stride = 0;
+    int tie_by_row = 0;
+    double tol;
+    int allow_shift;
+    int max_pairs;
+    int32_t *best_pos;   // position in candidate list
+    int32_t *best_row;   // library row (may be null)
+    double *best_score;
+    int32_t *n_pairs;
+    uint32_t *pairs;
+    int32_t *overflow;   // device counter of match-list overflows
+};
+void launch_best_match(solo_handle *h, const ScoreArgs &a);
+
+}  // namespace solo

@@ -1,0 +1,158 @@
+/* solo_b200.h — C-ABI of the B200-native ANN-SoLo hot path (libsolo_b200.so).
+ *
+ * Plain pointers and sizes only; every function returns 0 on success and a negative
+ * SOLO_E* code on failure, with a message available from solo_last_error(). All host
+ * buffers are owned by the caller (contiguous, little-endian); all device memory is owned
+ * by the handle. Calls are synchronous on return unless stated, one handle per GPU, not
+ * re-entrant. There is NO CPU fallback: without a CUDA device solo_create() fails.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/src/ann_solo/).
+ */
+#ifndef SOLO_B200_H
+#define SOLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct solo_handle solo_handle;
+
+enum {
+    SOLO_OK = 0,
+    SOLO_EINVAL = -1,    /* bad argument (maps to ValueError in the Python shim) */
+    SOLO_ECUDA = -2,     /* CUDA runtime / driver error */
+    SOLO_ENOMEM = -3,    /* device allocation failed */
+    SOLO_ESTATE = -4,    /* call order (e.g. search before a library/index is loaded) */
+    SOLO_ECAPACITY = -5  /* a fixed on-chip capacity was exceeded (reported, never truncated) */
+};
+
+enum { SOLO_TOL_DA = 0, SOLO_TOL_PPM = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Replaces faiss.StandardGpuResources() + the per-call new/delete of C++ objects in
+ * spectrum_match.pyx:83-108 (spectral_library.py:73-75). */
+int solo_create(int device, solo_handle **out);
+void solo_destroy(solo_handle *h);
+const char *solo_last_error(const solo_handle *h); /* h may be NULL: last create() error */
+const char *solo_version(void);
+/* Run all work on an externally owned cudaStream_t (e.g. torch's current stream) so that
+ * the caller's CUDA events bracket the kernels; NULL restores the handle's own stream. */
+int solo_set_stream(solo_handle *h, void *cuda_stream);
+/* Block until all work queued by this handle is complete. */
+int solo_synchronize(solo_handle *h);
+
+/* ---- K1: feature-hashed vectorisation -------------------------------------------------
+ * Replaces spectrum.py:166-214 spectrum_to_vector (+ :147-163 hash_idx, :123-143 get_dim),
+ * called per spectrum at spectral_library.py:157-161 and :435-440. */
+int solo_set_vectorizer(solo_handle *h, double min_mz, double max_mz, double bin_size, int hash_len);
+/* CSR batch -> (n, hash_len) float32 rows. mz is float32 or float64 (mz_is_f64); the bin
+ * arithmetic is carried out in that precision, as NumPy does for the array the caller holds. */
+int solo_vectorize(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity,
+                   const int64_t *offsets, int64_t n, int norm, float *out);
+/* The hashed slot of one m/z bin (for tests of the device LUT). */
+int solo_hash_slot(solo_handle *h, int64_t bin_idx, int32_t *slot);
+
+/* ---- library peak store (per precursor charge) ----------------------------------------
+ * Replaces the per-candidate marshalling of spectrum_match.pyx:72-85 and the lru_cache'd
+ * read_spectrum(idx, True) of spectral_library.py:449-454 / reader.py:218-246: processed library
+ * spectra are flattened once into a device-resident store. Row r of the store is position r of
+ * spec_info['charge'][charge]['id'] (reader.py:180-189). prec_mz32 is the float32 copy used by
+ * the window mask (reader.py:188-189), prec_mz the float64 value handed to the scorer. */
+int solo_load_library(solo_handle *h, int charge, const float *mz, const float *intensity,
+                      const uint8_t *peak_charge, const int64_t *offsets, const double *prec_mz,
+                      const float *prec_mz32, const int32_t *prec_charge, const uint8_t *valid,
+                      int64_t n);
+
+/* ---- IVF-Flat inner-product index (per precursor charge) ------------------------------
+ * Replaces faiss.IndexFlatIP + faiss.IndexIVFFlat(METRIC_INNER_PRODUCT):
+ *   train / add / write_index      spectral_library.py:167-181
+ *   read_index / nprobe / search   spectral_library.py:443-444, :490-497
+ *   reset                          spectral_library.py:191, :485 */
+int solo_ivf_set_centroids(solo_handle *h, int charge, const float *centroids, int nlist, int dim);
+/* spherical k-means on the device (Faiss `train`); x is (n, dim) float32 on the host. */
+int solo_ivf_train(solo_handle *h, int charge, const float *x, int64_t n, int dim, int nlist, int iters,
+                   uint64_t seed);
+int solo_ivf_get_centroids(solo_handle *h, int charge, float *centroids /* nlist*dim */);
+/* Append n dense rows; ids are insertion order (Faiss `add`). Rows holding NaN are skipped,
+ * as Faiss does for rows its quantizer cannot assign. */
+int solo_ivf_add(solo_handle *h, int charge, const float *x, int64_t n, int dim);
+/* Vectorise the loaded library store of this charge on the device and add every row. */
+int solo_ivf_add_library(solo_handle *h, int charge);
+int solo_ivf_reset(solo_handle *h, int charge);
+int solo_ivf_ntotal(solo_handle *h, int charge, int64_t *ntotal, int32_t *nlist, int32_t *dim);
+/* list_of_row[i] = inverted list holding row i (-1 = not stored). */
+int solo_ivf_get_assignment(solo_handle *h, int charge, int32_t *list_of_row);
+/* index.search(x, k) with index.nprobe = nprobe: I (nq,k) int64 padded with -1, D (nq,k)
+ * float32 descending (exact fp32 scores) padded with -inf; D may be NULL. */
+int solo_ivf_search(solo_handle *h, int charge, const float *queries, int nq, int dim, int k, int nprobe,
+                    int64_t *I, float *D);
+/* Coarse quantizer alone (IndexFlatIP.search on the centroids): probes (nq, nprobe) int32. */
+int solo_ivf_coarse(solo_handle *h, int charge, const float *queries, int nq, int dim, int nprobe,
+                    int32_t *probes);
+
+/* ---- K5: (shifted) dot product, greedy peak assignment, best candidate ----------------
+ * Replaces spectrum_match.pyx:28 get_best_match -> SpectrumMatch.cpp:8 SpectrumMatcher::dot,
+ * batched over queries. Candidates are rows of the loaded library store of `charge`, given as
+ * CSR (cand_off[nq+1], cand_ids). Outputs per query: best_pos = position inside its candidate
+ * list (first maximum wins, SpectrumMatch.cpp:118; -1 when the list is empty, where the
+ * reference caller skips the query, spectral_library.py:359), score, number of matched peak
+ * pairs and the pairs (query_peak, library_peak) in greedy order, max_pairs slots per query. */
+int solo_best_match_batch(solo_handle *h, int charge, const float *q_mz, const float *q_intensity,
+                          const int64_t *q_off, const double *q_prec_mz, int nq, const int32_t *cand_ids,
+                          const int64_t *cand_off, double fragment_mz_tolerance, int allow_shift,
+                          int max_pairs, int32_t *best_pos, double *best_score, int32_t *n_pairs,
+                          uint32_t *pairs);
+
+/* ---- fused open search for one batch --------------------------------------------------
+ * Replaces SpectralLibrary._search_batch (spectral_library.py:328-370) with
+ * _get_library_candidates (:372-455) for mode == 'open', config.mode == 'ann':
+ * vectorise -> IVF top-k -> precursor window AND valid (applied AFTER the top-k, :441-446)
+ * -> best match. use_ann = 0 gives the brute-force candidate set (every library row in the
+ * window; config.mode == 'bf', level-1 'std' search, or a charge without an index). */
+typedef struct {
+    int32_t use_ann;         /* 1: ANN top-k AND window; 0: window only */
+    int32_t k;               /* config.num_candidates */
+    int32_t nprobe;          /* config.num_probe */
+    int32_t tol_mode;        /* SOLO_TOL_DA / SOLO_TOL_PPM (precursor window) */
+    double tol_value;        /* precursor tolerance */
+    double fragment_mz_tolerance;
+    int32_t allow_shift;     /* config.allow_peak_shifts */
+    int32_t mz_is_f64;       /* dtype of the q_mz_vec array used for binning */
+    int32_t max_pairs;       /* slots per query in `pairs` */
+    int32_t reserved;
+} solo_search_params;
+
+/* Stage the queries of one batch on the device (host -> device copies, asynchronous). q_mz is
+ * the float32 m/z used by the scorer (pyx:86 astype(float32)); q_mz_vec (may equal q_mz) is the
+ * array used for binning in the precision the caller holds. */
+int solo_stage_queries(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
+                       const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64);
+/* Run the staged batch; results stay on the device. Asynchronous (stream-ordered). */
+int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p);
+/* Copy the results of the last solo_search_staged() to the host (synchronous).
+ * best_row: library row of the winner (-1 = no candidate); n_cand: candidates scored. */
+int solo_fetch_results(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs,
+                       uint32_t *pairs, int32_t *n_cand);
+/* stage + search + fetch. */
+int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, const float *q_mz,
+                      const void *q_mz_vec, const float *q_intensity, const int64_t *q_off,
+                      const double *q_prec_mz, int nq, int32_t *best_row, double *best_score,
+                      int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand);
+
+/* ---- instrumentation ------------------------------------------------------------------
+ * Per-stage device times (CUDA events on the launching stream) accumulated since the last
+ * reset, and the number of kernels this library launched. Stage names: solo_stage_name(i). */
+int solo_profile_enable(solo_handle *h, int on);
+int solo_profile_reset(solo_handle *h);
+int solo_profile_num_stages(void);
+const char *solo_stage_name(int stage);
+int solo_profile_get(solo_handle *h, int stage, double *ms_total, int64_t *launches, double *units);
+int64_t solo_kernel_launches(const solo_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLO_B200_H */
