@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <random>
 
 namespace solo {
@@ -799,13 +800,29 @@ static void append_sparse_rows(solo_handle *h, IvfIndex &ix, const float *d_x, i
     ix.nnz = new_nnz;
 }
 
-void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n) {
+__global__ void placeholder_assign_kernel(const uint8_t *__restrict__ bad, int64_t n, int32_t *__restrict__ row_list) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) row_list[i] = bad[i] ? -1 : 0;
+}
+
+void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n, bool assign) {
     SOLO_REQUIRE(ix.nlist > 0, SOLO_ESTATE, "index has no centroids (train or set_centroids first)");
     if (n <= 0) return;
     SOLO_REQUIRE(ix.ntotal + n < (int64_t)0x7fffffff, SOLO_ECAPACITY, "more than 2^31 rows");
     DevBuf &cnt = h->scratch[0], &bad = h->scratch[1], &best = h->scratch[2];
     const int64_t row0 = ix.ntotal;
     append_sparse_rows(h, ix, d_x, n, cnt, bad);
+    if (!assign) {  // training: rows are stored, lists are decided by the Lloyd iterations
+        ix.row_list.ensure_keep((row0 + n) * sizeof(int32_t), row0 * sizeof(int32_t), h->stream);
+        placeholder_assign_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(bad.as<uint8_t>(), n,
+                                                                        ix.row_list.as<int32_t>() + row0);
+        SOLO_CUDA(cudaGetLastError());
+        h->launches++;
+        ix.ntotal += n;
+        ix.dirty = true;
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        return;
+    }
     best.ensure((row0 + n) * sizeof(unsigned long long));
     SOLO_CUDA(cudaMemsetAsync(best.as<unsigned long long>() + row0, 0, n * sizeof(unsigned long long), h->stream));
     launch_coarse<1>(h, ix, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), row0, n,
@@ -1110,63 +1127,94 @@ centroid_update_kernel(const int64_t *__restrict__ list_off, const int32_t *__re
     for (int j = threadIdx.x; j < d; j += blockDim.x) cent[(int64_t)c * d + j] = (float)(s_acc[j] * inv);
 }
 
-void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
-               uint64_t seed) {
+// selected sparse rows -> dense centroid rows
+__global__ void densify_rows_kernel(const int32_t *__restrict__ rows, int nsel, const int64_t *__restrict__ row_off,
+                                    const uint16_t *__restrict__ row_idx, const float *__restrict__ row_val, int d,
+                                    float *__restrict__ out) {
+    const int c = blockIdx.x;
+    if (c >= nsel) return;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) out[(int64_t)c * d + j] = 0.f;
+    __syncthreads();
+    const int r = rows[c];
+    for (int64_t t = row_off[r] + threadIdx.x; t < row_off[r + 1]; t += blockDim.x)
+        out[(int64_t)c * d + row_idx[t]] = row_val[t];
+}
+
+// Spherical k-means (Faiss `train` for an inner-product IVF): the training rows are streamed to
+// the device once (`fill(r0, m, dst)` puts rows [r0, r0+m) into the dense device chunk `dst`) and
+// kept as sparse rows; every Lloyd iteration is one exact coarse-assignment pass plus one
+// deterministic centroid update. Leaves only centroids behind, like Faiss.
+void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist, int iters, uint64_t seed,
+                    const std::function<void(int64_t, int64_t, float *)> &fill) {
     SOLO_REQUIRE(n >= nlist, SOLO_EINVAL, "need at least nlist (%d) training rows, got %lld", nlist, (long long)n);
-    // initial centroids: nlist distinct finite rows, seeded
-    std::vector<int64_t> perm(n);
-    for (int64_t i = 0; i < n; ++i) perm[i] = i;
-    std::mt19937_64 rng(seed);
-    std::vector<float> cent((size_t)nlist * dim);
-    int got = 0;
-    for (int64_t i = 0; i < n && got < nlist; ++i) {
-        std::uniform_int_distribution<int64_t> dist(i, n - 1);
-        std::swap(perm[i], perm[dist(rng)]);
-        const float *r = h_x + perm[i] * dim;
-        bool ok = true;
-        for (int j = 0; j < dim && ok; ++j) ok = std::isfinite(r[j]);
-        if (ok) memcpy(cent.data() + (size_t)got++ * dim, r, dim * sizeof(float));
-    }
-    SOLO_REQUIRE(got == nlist, SOLO_EINVAL, "not enough finite training rows");
+    SOLO_REQUIRE(nlist > 0 && nlist <= IVF_MAX_NLIST, SOLO_EINVAL, "nlist must be in [1, %d]", IVF_MAX_NLIST);
+    SOLO_REQUIRE(dim > 0 && dim <= 1536, SOLO_EINVAL, "dim must be in [1, 1536] (got %d)", dim);
     ivf_reset(ix);
-    ivf_set_centroids(h, ix, cent.data(), nlist, dim);
-    // rows live on the device as sparse rows for the whole training
+    ix.nlist = nlist;
+    ix.dim = dim;
+    ix.cent.ensure((size_t)nlist * dim * sizeof(float));
+    ix.stats.ensure(4 * sizeof(int32_t));
+    SOLO_CUDA(cudaMemsetAsync(ix.stats.p, 0, 4 * sizeof(int32_t), h->stream));
     DevBuf &xd = h->scratch[19];
     const int64_t chunk = 1 << 17;
     xd.ensure((size_t)std::min(n, chunk) * dim * sizeof(float));
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         int64_t m = std::min(chunk, n - r0);
-        SOLO_CUDA(cudaMemcpyAsync(xd.p, h_x + r0 * dim, (size_t)m * dim * sizeof(float), cudaMemcpyHostToDevice,
-                                  h->stream));
-        ivf_add_device(h, ix, xd.as<float>(), m);  // sparse rows + assignment to the initial centroids
+        fill(r0, m, xd.as<float>());
+        ivf_add_device(h, ix, xd.as<float>(), m, /*assign=*/false);
     }
+    // initial centroids: nlist distinct storable rows, seeded partial Fisher-Yates
+    std::vector<int32_t> row_list(n);
+    SOLO_CUDA(cudaMemcpyAsync(row_list.data(), ix.row_list.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int32_t> good;
+    good.reserve(n);
+    for (int64_t i = 0; i < n; ++i)
+        if (row_list[i] >= 0) good.push_back((int32_t)i);
+    SOLO_REQUIRE((int64_t)good.size() >= nlist, SOLO_EINVAL, "not enough finite training rows");
+    std::mt19937_64 rng(seed);
+    for (int c = 0; c < nlist; ++c) {
+        std::uniform_int_distribution<int64_t> dist(c, (int64_t)good.size() - 1);
+        std::swap(good[c], good[dist(rng)]);
+    }
+    std::sort(good.begin(), good.begin() + nlist);
+    DevBuf &sel = h->scratch[0];
+    sel.ensure(nlist * sizeof(int32_t));
+    SOLO_CUDA(cudaMemcpyAsync(sel.p, good.data(), nlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    densify_rows_kernel<<<nlist, 128, 0, h->stream>>>(sel.as<int32_t>(), nlist, ix.row_off.as<int64_t>(),
+                                                      ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), dim,
+                                                      ix.cent.as<float>());
+    SOLO_CUDA(cudaGetLastError());
+    h->launches++;
     for (int it = 0; it < iters; ++it) {
+        DevBuf &best = h->scratch[2];
+        best.ensure(n * sizeof(unsigned long long));
+        SOLO_CUDA(cudaMemsetAsync(best.p, 0, n * sizeof(unsigned long long), h->stream));
+        launch_coarse<1>(h, ix, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), 0, n,
+                         nullptr, best.as<unsigned long long>());
+        decode_assign_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(best.as<unsigned long long>(), nullptr, n,
+                                                                    ix.row_list.as<int32_t>());
+        SOLO_CUDA(cudaGetLastError());
+        ix.dirty = true;
         ivf_finalize(h, ix);
         centroid_update_kernel<<<nlist, 256, dim * sizeof(double), h->stream>>>(
             ix.list_off.as<int64_t>(), ix.list_ids.as<int32_t>(), ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(),
             ix.row_val.as<float>(), dim, ix.cent.as<float>());
         SOLO_CUDA(cudaGetLastError());
-        h->launches++;
-        if (it + 1 < iters) {
-            // re-assign the stored sparse rows against the updated centroids
-            DevBuf &best = h->scratch[2];
-            best.ensure(n * sizeof(unsigned long long));
-            SOLO_CUDA(cudaMemsetAsync(best.p, 0, n * sizeof(unsigned long long), h->stream));
-            launch_coarse<1>(h, ix, ix.row_off.as<int64_t>(), ix.row_idx.as<uint16_t>(), ix.row_val.as<float>(), 0, n,
-                             nullptr, best.as<unsigned long long>());
-            decode_assign_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(best.as<unsigned long long>(), nullptr, n,
-                                                                        ix.row_list.as<int32_t>());
-            SOLO_CUDA(cudaGetLastError());
-            h->launches += 2;
-            ix.dirty = true;
-        }
+        h->launches += 3;
     }
-    // training leaves only centroids behind (Faiss `train` does not add vectors)
     std::vector<float> out((size_t)nlist * dim);
     SOLO_CUDA(cudaMemcpyAsync(out.data(), ix.cent.p, out.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     SOLO_CUDA(cudaStreamSynchronize(h->stream));
     ivf_reset(ix);
     ivf_set_centroids(h, ix, out.data(), nlist, dim);
+}
+
+void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
+               uint64_t seed) {
+    ivf_train_rows(h, ix, n, dim, nlist, iters, seed, [&](int64_t r0, int64_t m, float *dst) {
+        SOLO_CUDA(cudaMemcpyAsync(dst, h_x + r0 * dim, (size_t)m * dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    });
 }
 
 }  // namespace solo

@@ -1,5 +1,7 @@
 // IVF-Flat inner-product index: declarations shared by ivf.cu / ivf_tc.cu / solo_api.cu.
 #pragma once
+#include <functional>
+
 #include "solo_common.cuh"
 
 namespace solo {
@@ -57,7 +59,9 @@ struct IvfSearchArgs {
 // exclusive scan of n int32 counts into n+1 int64 offsets (single CTA)
 void scan_counts_i32(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off);
 void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nlist, int dim);
-void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n);  // d_x (n, dim) on device
+void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n, bool assign = true);  // d_x on device
+void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist, int iters, uint64_t seed,
+                    const std::function<void(int64_t, int64_t, float *)> &fill);
 void ivf_finalize(solo_handle *h, IvfIndex &ix);
 void ivf_reset(IvfIndex &ix);
 void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a);

@@ -214,7 +214,9 @@ void solo_destroy(solo_handle *h) {
     }
     rel(h->q_mz); rel(h->q_mz_vec); rel(h->q_int); rel(h->q_off); rel(h->q_prec_mz);
     for (auto &b : h->scratch) rel(b);
-    rel(h->r_best_row); rel(h->r_best_score); rel(h->r_n_pairs); rel(h->r_pairs); rel(h->r_n_cand);
+    rel(h->r_best_row); rel(h->r_best_score); rel(h->r_n_pairs); rel(h->r_pairs); rel(h->r_n_cand); rel(h->r_ovf);
+    for (auto &kv : h->parked)
+        for (auto &b : kv.second.b) rel(b);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -357,6 +359,20 @@ int solo_ivf_train(solo_handle *h, int charge, const float *x, int64_t n, int di
     return guarded(h, [&] {
         SOLO_REQUIRE(nlist > 0 && nlist <= IVF_MAX_NLIST, SOLO_EINVAL, "nlist must be in [1, %d]", IVF_MAX_NLIST);
         ivf_train(h, get_ivf(h, charge, false), x, n, dim, nlist, std::max(iters, 0), seed);
+    });
+}
+
+int solo_ivf_train_library(solo_handle *h, int charge, int nlist, int iters, uint64_t seed) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        LibraryStore &L = get_lib(h, charge);
+        std::vector<int64_t> hoff(L.n + 1);
+        SOLO_CUDA(cudaMemcpy(hoff.data(), L.off.p, (L.n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        ivf_train_rows(h, get_ivf(h, charge, false), L.n, h->hash_len, nlist, std::max(iters, 0), seed,
+                       [&](int64_t r0, int64_t m, float *dst) {
+                           launch_vectorize(h, L.mz.p, 0, L.inten.as<float>(), L.off.as<int64_t>() + r0, m,
+                                            hoff[r0 + m] - hoff[r0], 1, dst, nullptr, 0);
+                       });
     });
 }
 
@@ -583,6 +599,31 @@ int solo_best_match_batch(solo_handle *h, int charge, const float *q_mz, const f
 
 // ---------------------------------------------------------------- fused open search
 
+static void slot_fields(solo_handle *h, DevBuf **f) {
+    DevBuf *all[11] = {&h->q_mz, &h->q_mz_vec, &h->q_int, &h->q_off, &h->q_prec_mz, &h->r_best_row,
+                       &h->r_best_score, &h->r_n_pairs, &h->r_pairs, &h->r_n_cand, &h->r_ovf};
+    for (int i = 0; i < 11; ++i) f[i] = all[i];
+}
+
+int solo_select_slot(solo_handle *h, int slot) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        if (slot == h->active_slot) return;
+        DevBuf *f[11];
+        slot_fields(h, f);
+        solo_handle::Slot &out = h->parked[h->active_slot];
+        out.nq = h->nq; out.q_peaks = h->q_peaks; out.q_max_peaks = h->q_max_peaks; out.q_mz_is_f64 = h->q_mz_is_f64;
+        out.r_nq = h->r_nq; out.r_max_pairs = h->r_max_pairs;
+        for (int i = 0; i < 11; ++i) out.b[i] = *f[i];
+        solo_handle::Slot in = h->parked[slot];  // empty when new
+        h->parked.erase(slot);
+        h->nq = in.nq; h->q_peaks = in.q_peaks; h->q_max_peaks = in.q_max_peaks; h->q_mz_is_f64 = in.q_mz_is_f64;
+        h->r_nq = in.r_nq; h->r_max_pairs = in.r_max_pairs;
+        for (int i = 0; i < 11; ++i) *f[i] = in.b[i];
+        h->active_slot = slot;
+    });
+}
+
 int solo_stage_queries(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
                        const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
     if (!h) return SOLO_EINVAL;
@@ -599,7 +640,7 @@ int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p) 
         SOLO_REQUIRE(p->max_pairs > 0, SOLO_EINVAL, "max_pairs must be positive");
         ensure_results(h, nq, p->max_pairs);
         if (nq == 0) return;
-        DevBuf &ovf = h->scratch[22];
+        DevBuf &ovf = h->r_ovf;
         ovf.ensure(16);
         SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
         ScoreArgs a;
@@ -698,7 +739,7 @@ int solo_fetch_results(solo_handle *h, int32_t *best_row, double *best_score, in
             cp(n_pairs, h->r_n_pairs, (size_t)nq * 4);
             cp(pairs, h->r_pairs, (size_t)nq * h->r_max_pairs * 8);
             cp(n_cand, h->r_n_cand, (size_t)nq * 4);
-            cp(&n_over, h->scratch[22], 4);
+            cp(&n_over, h->r_ovf, 4);
         }
         SOLO_CUDA(cudaStreamSynchronize(h->stream));
         SOLO_REQUIRE(n_over == 0, SOLO_ECAPACITY,

@@ -189,8 +189,17 @@ struct solo_handle {
     // scratch
     solo::DevBuf scratch[24];
     // results of the last staged search
-    solo::DevBuf r_best_row, r_best_score, r_n_pairs, r_pairs, r_n_cand;
+    solo::DevBuf r_best_row, r_best_score, r_n_pairs, r_pairs, r_n_cand, r_ovf;
     int r_nq = 0, r_max_pairs = 0;
+    // query slots: the staged batch + its results above belong to the active slot; the others are parked
+    struct Slot {
+        int nq = 0;
+        int64_t q_peaks = 0;
+        int q_max_peaks = 0, q_mz_is_f64 = 0, r_nq = 0, r_max_pairs = 0;
+        solo::DevBuf b[11];
+    };
+    int active_slot = 0;
+    std::map<int, Slot> parked;
 };
 
 namespace solo {

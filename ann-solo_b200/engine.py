@@ -1,0 +1,257 @@
+"""NumPy-facing wrapper of one libsolo_b200 handle (one per GPU).
+
+All compute happens in the hand-written sm_100a kernels behind the C-ABI; this module only
+checks dtypes/contiguity and hands out pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import SearchParams, SoloError, TOL_DA, TOL_PPM
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class SoloEngine:
+    """Device-side state of the hot path: vectoriser LUT, per-charge library peak stores and
+    per-charge IVF indexes (replaces the faiss resources and Cython matcher objects of
+    reference spectral_library.py:73-87 and spectrum_match.pyx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.solo_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SoloError(rc, self._lib.solo_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.hash_len = 800
+        self._lib_max_peaks = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.solo_last_error(self._h).decode()
+            if rc == _lib.SOLO_EINVAL:
+                raise ValueError(msg)
+            raise SoloError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.solo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self._lib.solo_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._check(self._lib.solo_synchronize(self._h))
+
+    # ------------------------------------------------------------------ K1
+    def set_vectorizer(self, min_mz: float, max_mz: float, bin_size: float, hash_len: int):
+        self._check(self._lib.solo_set_vectorizer(self._h, min_mz, max_mz, bin_size, int(hash_len)))
+        self.hash_len = int(hash_len)
+
+    def hash_slot(self, bin_idx: int) -> int:
+        s = C.c_int32()
+        self._check(self._lib.solo_hash_slot(self._h, int(bin_idx), C.byref(s)))
+        return s.value
+
+    def vectorize(self, mz: np.ndarray, intensity: np.ndarray, offsets: np.ndarray, norm: bool = True) -> np.ndarray:
+        """Batched spectrum_to_vector. The bin arithmetic follows mz.dtype (float32 or float64)."""
+        is64 = mz.dtype == np.float64
+        mz = _c(mz, np.float64 if is64 else np.float32)
+        intensity = _c(intensity, np.float32)
+        offsets = _c(offsets, np.int64)
+        n = len(offsets) - 1
+        out = np.empty((n, self.hash_len), np.float32)
+        self._check(self._lib.solo_vectorize(self._h, _ptr(mz), int(is64), _ptr(intensity), _ptr(offsets), n,
+                                             int(norm), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ library store
+    def load_library(self, charge: int, store: dict):
+        """store: peak-store dict (mz f32, inten f32, chg u8, off i64, prec_mz f64, prec_z i32,
+        optional valid u8, optional prec_mz32 f32)."""
+        mz = _c(store["mz"], np.float32)
+        inten = _c(store["inten"], np.float32)
+        chg = _c(store["chg"], np.uint8) if store.get("chg") is not None else None
+        off = _c(store["off"], np.int64)
+        pm = _c(store["prec_mz"], np.float64)
+        pm32 = _c(store["prec_mz32"], np.float32) if store.get("prec_mz32") is not None else None
+        pz = _c(store["prec_z"], np.int32)
+        valid = _c(store["valid"], np.uint8) if store.get("valid") is not None else None
+        n = len(off) - 1
+        self._check(self._lib.solo_load_library(self._h, int(charge), _ptr(mz), _ptr(inten), _ptr(chg), _ptr(off),
+                                                _ptr(pm), _ptr(pm32), _ptr(pz), _ptr(valid), n))
+        self._lib_max_peaks[int(charge)] = int(np.diff(off).max()) if n else 0
+
+    # ------------------------------------------------------------------ IVF
+    def ivf_set_centroids(self, charge: int, centroids: np.ndarray):
+        c = _c(centroids, np.float32)
+        self._check(self._lib.solo_ivf_set_centroids(self._h, int(charge), _ptr(c), c.shape[0], c.shape[1]))
+
+    def ivf_train(self, charge: int, x: np.ndarray, nlist: int, iters: int = 10, seed: int = 1234):
+        x = _c(x, np.float32)
+        self._check(self._lib.solo_ivf_train(self._h, int(charge), _ptr(x), x.shape[0], x.shape[1], int(nlist),
+                                             int(iters), int(seed)))
+
+    def ivf_train_library(self, charge: int, nlist: int, iters: int = 10, seed: int = 1234):
+        """k-means on the loaded library store of `charge`, vectorised on the device."""
+        self._check(self._lib.solo_ivf_train_library(self._h, int(charge), int(nlist), int(iters), int(seed)))
+
+    def ivf_info(self, charge: int):
+        n, nl, d = C.c_int64(), C.c_int32(), C.c_int32()
+        self._check(self._lib.solo_ivf_ntotal(self._h, int(charge), C.byref(n), C.byref(nl), C.byref(d)))
+        return n.value, nl.value, d.value
+
+    def ivf_get_centroids(self, charge: int) -> np.ndarray:
+        _, nl, d = self.ivf_info(charge)
+        out = np.empty((nl, d), np.float32)
+        self._check(self._lib.solo_ivf_get_centroids(self._h, int(charge), _ptr(out)))
+        return out
+
+    def ivf_add(self, charge: int, x: np.ndarray):
+        x = _c(x, np.float32)
+        self._check(self._lib.solo_ivf_add(self._h, int(charge), _ptr(x), x.shape[0], x.shape[1]))
+
+    def ivf_add_library(self, charge: int):
+        self._check(self._lib.solo_ivf_add_library(self._h, int(charge)))
+
+    def ivf_reset(self, charge: int):
+        self._check(self._lib.solo_ivf_reset(self._h, int(charge)))
+
+    def ivf_assignment(self, charge: int) -> np.ndarray:
+        n, _, _ = self.ivf_info(charge)
+        out = np.empty(n, np.int32)
+        self._check(self._lib.solo_ivf_get_assignment(self._h, int(charge), _ptr(out)))
+        return out
+
+    def ivf_search(self, charge: int, queries: np.ndarray, k: int, nprobe: int, want_d: bool = True):
+        q = _c(queries, np.float32)
+        nq, d = q.shape
+        I = np.empty((nq, k), np.int64)
+        D = np.empty((nq, k), np.float32) if want_d else None
+        self._check(self._lib.solo_ivf_search(self._h, int(charge), _ptr(q), nq, d, int(k), int(nprobe), _ptr(I),
+                                              _ptr(D)))
+        return D, I
+
+    def ivf_coarse(self, charge: int, queries: np.ndarray, nprobe: int) -> np.ndarray:
+        q = _c(queries, np.float32)
+        nq, d = q.shape
+        _, nl, _ = self.ivf_info(charge)
+        out = np.empty((nq, min(nprobe, nl)), np.int32)
+        self._check(self._lib.solo_ivf_coarse(self._h, int(charge), _ptr(q), nq, d, int(nprobe), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ K5
+    def best_match_batch(self, charge: int, q: dict, cand_ids: np.ndarray, cand_off: np.ndarray, tol: float,
+                         allow_shift: bool, max_pairs: Optional[int] = None):
+        qmz = _c(q["mz"], np.float32)
+        qin = _c(q["inten"], np.float32)
+        qoff = _c(q["off"], np.int64)
+        qpm = _c(q["prec_mz"], np.float64)
+        cand_ids = _c(cand_ids, np.int32)
+        cand_off = _c(cand_off, np.int64)
+        nq = len(qoff) - 1
+        if max_pairs is None:
+            max_pairs = max(1, int(np.diff(qoff).max()) if nq else 1)
+        bp = np.empty(nq, np.int32)
+        bs = np.empty(nq, np.float64)
+        npairs = np.empty(nq, np.int32)
+        pairs = np.zeros((nq, max_pairs, 2), np.uint32)
+        self._check(self._lib.solo_best_match_batch(self._h, int(charge), _ptr(qmz), _ptr(qin), _ptr(qoff), _ptr(qpm),
+                                                    nq, _ptr(cand_ids), _ptr(cand_off), float(tol), int(allow_shift),
+                                                    int(max_pairs), _ptr(bp), _ptr(bs), _ptr(npairs), _ptr(pairs)))
+        return bp, bs, npairs, pairs
+
+    # ------------------------------------------------------------------ fused search
+    @staticmethod
+    def make_params(use_ann: bool, k: int, nprobe: int, tol_value: float, tol_mode: str, fragment_mz_tolerance: float,
+                    allow_shift: bool, max_pairs: int = 64, mz_is_f64: bool = False) -> SearchParams:
+        if tol_mode not in ("Da", "ppm"):
+            raise ValueError("Unknown precursor tolerance mode")  # reference spectral_library.py:429
+        return SearchParams(int(use_ann), int(k), int(nprobe), TOL_DA if tol_mode == "Da" else TOL_PPM,
+                            float(tol_value), float(fragment_mz_tolerance), int(allow_shift), int(mz_is_f64),
+                            int(max_pairs), 0)
+
+    def select_slot(self, slot: int):
+        """Make `slot` the active query slot (staged batch + results); others stay parked in HBM."""
+        self._check(self._lib.solo_select_slot(self._h, int(slot)))
+        self._slot_state = getattr(self, "_slot_state", {})
+        self._slot_state[getattr(self, "_slot", 0)] = (getattr(self, "_staged", None), getattr(self, "_staged_nq", 0),
+                                                       getattr(self, "_staged_max_pairs", 0))
+        self._slot = int(slot)
+        self._staged, self._staged_nq, self._staged_max_pairs = self._slot_state.get(self._slot, (None, 0, 0))
+
+    def stage_queries(self, q: dict, mz_vec: Optional[np.ndarray] = None):
+        """Queue the host->device copies of one query batch. The arrays must stay alive until the
+        next synchronising call (they are kept referenced here)."""
+        qmz = _c(q["mz"], np.float32)
+        qin = _c(q["inten"], np.float32)
+        qoff = _c(q["off"], np.int64)
+        qpm = _c(q["prec_mz"], np.float64)
+        is64 = mz_vec is not None and mz_vec.dtype == np.float64
+        if mz_vec is not None:
+            mz_vec = _c(mz_vec, np.float64 if is64 else np.float32)
+        self._staged = (qmz, qin, qoff, qpm, mz_vec)
+        self._staged_nq = len(qoff) - 1
+        self._check(self._lib.solo_stage_queries(self._h, _ptr(qmz), _ptr(mz_vec), _ptr(qin), _ptr(qoff), _ptr(qpm),
+                                                 self._staged_nq, int(is64)))
+
+    def search_staged(self, charge: int, params: SearchParams):
+        self._check(self._lib.solo_search_staged(self._h, int(charge), C.byref(params)))
+        self._staged_max_pairs = params.max_pairs
+
+    def fetch_results(self, out: Optional[dict] = None) -> dict:
+        nq, mp = self._staged_nq, self._staged_max_pairs
+        if out is None:
+            out = dict(best_row=np.empty(nq, np.int32), score=np.empty(nq, np.float64),
+                       n_pairs=np.empty(nq, np.int32), pairs=np.empty((nq, mp, 2), np.uint32),
+                       n_cand=np.empty(nq, np.int32))
+        self._check(self._lib.solo_fetch_results(self._h, _ptr(out["best_row"]), _ptr(out["score"]),
+                                                 _ptr(out["n_pairs"]), _ptr(out["pairs"]), _ptr(out["n_cand"])))
+        return out
+
+    def search_batch(self, charge: int, params: SearchParams, q: dict, mz_vec: Optional[np.ndarray] = None,
+                     out: Optional[dict] = None) -> dict:
+        """One batch through the whole hot path with host buffers (vectorise -> IVF top-k ->
+        window mask -> best match)."""
+        self.stage_queries(q, mz_vec)
+        self.search_staged(charge, params)
+        return self.fetch_results(out)
+
+    # ------------------------------------------------------------------ instrumentation
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.solo_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(self._lib.solo_profile_reset(self._h))
+
+    def profile(self) -> dict:
+        out = {}
+        for s in range(self._lib.solo_profile_num_stages()):
+            ms, n, u = C.c_double(), C.c_int64(), C.c_double()
+            self._check(self._lib.solo_profile_get(self._h, s, C.byref(ms), C.byref(n), C.byref(u)))
+            out[self._lib.solo_stage_name(s).decode()] = dict(ms=ms.value, launches=n.value, units=u.value)
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.solo_kernel_launches(self._h))

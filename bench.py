@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — query spectra/s through the cascade open-search hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/)
+
+A step is one pass of the hot path (vectorise -> IVF top-k -> precursor window -> shifted dot)
+over one batch of synthetic queries per rank: BASELINE.json configs[1] ("C2": 16,384 queries vs
+a 3 M-vector library, charges 2-4, nprobe 1024, top-1024, 500 Da open window). Weak scaling: every
+rank holds a replica of the library/index (mode A) and its own 16,384-query batch.
+`value` is timed with the batch already resident in HBM, `e2e` through the C-ABI with host
+buffers (H2D of the queries and D2H of the results inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_targets, decoy_fraction, queries per rank, nlist, nprobe, k, cpu sample queries)
+    "c2": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=512,
+               label="C2: 16,384 queries vs 3M-vector library (2M targets + 1M decoys), charges 2-4"),
+    "c2s": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=4096, nprobe=1024, k=1024, cpu_sample=128,
+                label="C2 (second point, nlist 4096)"),
+    "c1": dict(n_targets=200_000, decoys=0.5, nq=16384, nlist=256, nprobe=128, k=1024, cpu_sample=512,
+               label="C1: 16,384 queries vs 200k+100k-decoy library, charges 2-4"),
+    "tiny": dict(n_targets=20_000, decoys=0.5, nq=1024, nlist=64, nprobe=16, k=128, cpu_sample=256,
+                 label="tiny smoke workload"),
+}
+OPEN_TOL, OPEN_MODE, FRAG_TOL = 500.0, "Da", 0.02
+TRAIN_ITERS = 2
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(wl, rank):
+    from ann_solo_b200 import synth
+    t0 = time.time()
+    lib = synth.make_library(wl["n_targets"], decoy_fraction=wl["decoys"], seed=1, decoy_seed=2)
+    per_charge = synth.split_by_charge(lib)
+    queries = synth.make_queries(lib, wl["nq"], seed=3 + rank)
+    q_by_charge = {}
+    for z in sorted(per_charge):
+        sel = np.flatnonzero(queries["prec_z"] == z)
+        if len(sel):
+            q_by_charge[z] = synth.take_spectra(queries, sel)
+    log(f"synthetic data: {len(lib['prec_mz'])} library spectra, {wl['nq']} queries/rank in {time.time() - t0:.1f}s")
+    return lib, per_charge, q_by_charge
+
+
+def pinned_copy(torch, a):
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def run_solo(args, wl, rank, world, local_rank):
+    import torch
+    from ann_solo_b200.engine import SoloEngine
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib, per_charge, q_by_charge = make_data(wl, rank)
+    eng = SoloEngine(local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    t0 = time.time()
+    charges = sorted(q_by_charge)
+    n_vec = {}
+    for z in charges:
+        store, _ = per_charge[z]
+        eng.load_library(z, store)
+        nlist = min(wl["nlist"], max(1, len(store["prec_mz"]) // 39))
+        eng.ivf_train_library(z, nlist, iters=TRAIN_ITERS, seed=4)
+        eng.ivf_add_library(z)
+        n_vec[z] = (len(store["prec_mz"]), nlist)
+    eng.synchronize()
+    log(f"index build (k-means {TRAIN_ITERS} it. + add, all charges): {time.time() - t0:.1f}s  {n_vec}")
+
+    max_pairs = 50
+    params = SoloEngine.make_params(True, wl["k"], wl["nprobe"], OPEN_TOL, OPEN_MODE, FRAG_TOL, True, max_pairs)
+    # pinned host copies of the queries and of the result buffers (e2e path)
+    pin_keep, host_q, host_out = [], {}, {}
+    h2d_bytes = d2h_bytes = 0
+    for z in charges:
+        q = q_by_charge[z]
+        hq = {}
+        for key in ("mz", "inten", "off", "prec_mz"):
+            t, hq[key] = pinned_copy(torch, q[key])
+            pin_keep.append(t)
+            h2d_bytes += hq[key].nbytes
+        host_q[z] = hq
+        nq = len(q["prec_mz"])
+        out = {}
+        for key, shape, dt in (("best_row", (nq,), np.int32), ("score", (nq,), np.float64),
+                               ("n_pairs", (nq,), np.int32), ("pairs", (nq, max_pairs, 2), np.uint32),
+                               ("n_cand", (nq,), np.int32)):
+            t = torch.empty(shape, dtype=getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))).pin_memory()
+            pin_keep.append(t)
+            out[key] = t.numpy().view(dt)
+            d2h_bytes += out[key].nbytes
+        host_out[z] = out
+    nq_rank = sum(len(q_by_charge[z]["prec_mz"]) for z in charges)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM (one slot per charge), compute only
+    for z in charges:
+        eng.select_slot(z)
+        eng.stage_queries(host_q[z])
+    eng.synchronize()
+
+    def step_resident():
+        for z in charges:
+            eng.select_slot(z)
+            eng.search_staged(z, params)
+
+    def step_e2e():
+        for z in charges:
+            eng.select_slot(z)
+            eng.search_batch(z, params, host_q[z], out=host_out[z])
+
+    def timed(step_fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        if profile:
+            eng.profile_reset()
+            eng.profile_enable(True)
+        launches0 = eng.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(steps):
+                step_fn()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        prof = eng.profile() if profile else None
+        eng.profile_enable(False)
+        launches = eng.kernel_launches() - launches0
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), prof, launches, clk.summary()
+
+    ms_res, prof, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    value = world * nq_rank * args.steps / (ms_res / 1e3)
+    e2e = world * nq_rank * args.steps / (ms_e2e / 1e3)
+
+    # ---- sanity: the e2e results of the last step are real
+    n_match = int(sum((host_out[z]["best_row"] >= 0).sum() for z in charges))
+    assert n_match > 0.5 * nq_rank, f"only {n_match} of {nq_rank} queries matched"
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (K3 list scan): algorithmic flops 2*d*S per query
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
+    scan = prof["scan"]
+    scan_ms_per_launch = scan["ms"] / max(scan["launches"], 1)
+    flops_per_launch = scan["units"] / max(scan["launches"], 1)
+    achieved = flops_per_launch / (scan_ms_per_launch * 1e-3) / 1e12 if scan_ms_per_launch > 0 else 0.0
+    roofline = {"kernel": "k3_list_scan", "bound": "tensor", "achieved": round(achieved, 3), "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 5), "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": round(scan_ms_per_launch, 4), "launches": scan["launches"],
+                "share_of_step": round(scan["ms"] / ms_res, 4)}
+    stages = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
+
+    cpu = cpu_baseline(wl, per_charge, q_by_charge, eng) if not args.no_cpu_baseline else None
+    line = {
+        "metric": "query spectra/sec, cascade open search", "value": round(value, 1), "unit": "spectra/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "queries_per_rank_per_step": nq_rank, "nlist": wl["nlist"],
+                   "nprobe": wl["nprobe"], "k": wl["k"], "open_window": f"{OPEN_TOL} {OPEN_MODE}",
+                   "fragment_tol": FRAG_TOL, "parallelism": f"queries partitioned x{world}, library replicated",
+                   "l2": "index and peak store (>1 GB) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": round(e2e, 1), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stages,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_pipeline(o, store, q, cent, assign, nlist, wl, charge, threads, use_ref):
+    """The reference's CPU path for one batch of one charge: vectorise, IVF-Flat search (dense
+    SIMD scan like Faiss), post-top-k window mask, SpectrumMatcher::dot (the reference's own
+    compiled core when oracle/_ref exists)."""
+    qv = o.vectorize(q["mz"], q["inten"], q["off"])
+    _, ann = o.ivf_search(qv, cent, store["_list_off"], store["_list_ids"], store["_list_vecs"],
+                          min(wl["nprobe"], nlist), wl["k"], simd=True, n_threads=threads)
+    cand, coff = o.candidates(q["prec_mz"], store["prec_mz"].astype(np.float32), store["valid"], charge, OPEN_TOL,
+                              OPEN_MODE, ann)
+    if use_ref:
+        return o.ref_best_match_batch(q, store, cand, coff, FRAG_TOL, True, n_threads=threads)
+    return o.best_match_batch(q, store, cand, coff, FRAG_TOL, True, sort_mode=0, n_threads=threads)
+
+
+def cpu_baseline(wl, per_charge, q_by_charge, eng):
+    """Bounded sample of the same workload on the host cores, same centroids/lists as the GPU."""
+    from ann_solo_b200 import synth
+    from oracle import solo_oracle as o  # cpu_baseline leg only
+    threads = o.num_threads()
+    use_ref = o.have_ref()
+    total_q, total_s = 0, 0.0
+    n_all = sum(len(q["prec_mz"]) for q in q_by_charge.values())
+    for z, q in q_by_charge.items():
+        take = max(8, int(round(wl["cpu_sample"] * len(q["prec_mz"]) / n_all)))
+        qs = synth.take_spectra(q, np.arange(min(take, len(q["prec_mz"]))))
+        store = dict(per_charge[z][0])
+        cent = eng.ivf_get_centroids(z)
+        assign = eng.ivf_assignment(z)
+        x = o.vectorize(store["mz"], store["inten"], store["off"])
+        store["_list_off"], store["_list_ids"], store["_list_vecs"] = o.build_lists(x, assign, len(cent))
+        del x
+        t0 = time.perf_counter()
+        cpu_pipeline(o, store, qs, cent, assign, len(cent), wl, z, threads, use_ref)
+        total_s += time.perf_counter() - t0
+        total_q += len(qs["prec_mz"])
+        del store
+    return {"value": round(total_q / total_s, 2), "unit": "spectra/s", "cores": threads,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{total_q} queries of the same workload (all charges), vectorise + restated Faiss IVF-Flat "
+                      f"(dense SIMD scan, OpenMP) + window + {'reference SpectrumMatch.cpp' if use_ref else 'ported scorer'}"
+                      f" on {threads} threads, {total_s:.1f}s"}
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0
+    only). The index is built on the CPU too (same seeded k-means recipe, fast exact assignment)."""
+    if rank != 0:
+        return
+    from ann_solo_b200 import synth
+    from oracle import solo_oracle as o  # reference arm
+    threads = o.num_threads()
+    use_ref = o.have_ref()
+    lib, per_charge, q_by_charge = make_data(wl, 0)
+    stores, cents = {}, {}
+    t0 = time.time()
+    for z in q_by_charge:
+        store = dict(per_charge[z][0])
+        x = o.vectorize(store["mz"], store["inten"], store["off"])
+        nlist = min(wl["nlist"], max(1, len(x) // 39))
+        cent = o.kmeans(x, nlist, seed=4, iters=TRAIN_ITERS)
+        assign = o.ivf_assign(x, cent)
+        store["_list_off"], store["_list_ids"], store["_list_vecs"] = o.build_lists(x, assign, nlist)
+        del x
+        stores[z], cents[z] = store, cent
+    log(f"CPU index build: {time.time() - t0:.1f}s")
+    n_all = sum(len(q["prec_mz"]) for q in q_by_charge.values())
+    sample = max(32, wl["cpu_sample"] // 2)
+
+    def step(i):
+        n = 0
+        for z, q in q_by_charge.items():
+            take = max(4, int(round(sample * len(q["prec_mz"]) / n_all)))
+            lo = (i * take) % max(1, len(q["prec_mz"]) - take)
+            qs = synth.take_spectra(q, np.arange(lo, lo + take))
+            cpu_pipeline(o, stores[z], qs, cents[z], None, len(cents[z]), wl, z, threads, use_ref)
+            n += take
+        return n
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    n = sum(step(args.warmup + i) for i in range(args.steps))
+    dt = time.perf_counter() - t0
+    v = round(n / dt, 2)
+    desc = {"value": v, "unit": "spectra/s", "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"{n // args.steps} queries per step (bounded sample of the {wl['nq']}-query batch)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "query spectra/sec, cascade open search", "value": v, "unit": "spectra/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "nlist": wl["nlist"], "nprobe": wl["nprobe"], "k": wl["k"],
+                   "open_window": f"{OPEN_TOL} {OPEN_MODE}", "fragment_tol": FRAG_TOL},
+        "cpu_baseline": desc,
+        "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="solo", choices=["solo", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SOLO_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_solo(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,9 @@ int solo_ivf_set_centroids(solo_handle *h, int charge, const float *centroids, i
 /* spherical k-means on the device (Faiss `train`); x is (n, dim) float32 on the host. */
 int solo_ivf_train(solo_handle *h, int charge, const float *x, int64_t n, int dim, int nlist, int iters,
                    uint64_t seed);
+/* the same, with the loaded library store of this charge vectorised on the device as the
+ * training set (what _create_ann_indexes feeds to train(), spectral_library.py:152-178). */
+int solo_ivf_train_library(solo_handle *h, int charge, int nlist, int iters, uint64_t seed);
 int solo_ivf_get_centroids(solo_handle *h, int charge, float *centroids /* nlist*dim */);
 /* Append n dense rows; ids are insertion order (Faiss `add`). Rows holding NaN are skipped,
  * as Faiss does for rows its quantizer cannot assign. */
@@ -125,6 +128,10 @@ typedef struct {
     int32_t reserved;
 } solo_search_params;
 
+/* The staged batch and its results live in a "slot"; slot 0 is active after solo_create().
+ * Selecting another slot parks the current one on the device, so several batches (e.g. one per
+ * precursor charge) can stay resident in HBM and be searched back to back. */
+int solo_select_slot(solo_handle *h, int slot);
 /* Stage the queries of one batch on the device (host -> device copies, asynchronous). q_mz is
  * the float32 m/z used by the scorer (pyx:86 astype(float32)); q_mz_vec (may equal q_mz) is the
  * array used for binning in the precision the caller holds. */

@@ -199,12 +199,18 @@ def ip(a, b) -> float:
     return float(port().oracle_ip(_p(a, _f32p), _p(b, _f32p), C.c_int(len(a))))
 
 
-def ivf_assign(x, centroids):
+def ivf_assign(x, centroids, fast=True, n_threads=0):
+    """List of every row: best centroid under (score desc, id asc); -1 for NaN rows. fast=True
+    uses the transposed sparse-aware loop (bit-identical, see solo_oracle.cpp)."""
     x = np.ascontiguousarray(x, np.float32)
     centroids = np.ascontiguousarray(centroids, np.float32)
     out = np.empty(len(x), np.int32)
-    port().oracle_ivf_assign(_p(x, _f32p), C.c_int64(len(x)), C.c_int(x.shape[1]), _p(centroids, _f32p),
-                             C.c_int(len(centroids)), _p(out, _i32p))
+    if fast:
+        port().oracle_ivf_assign_fast(_p(x, _f32p), C.c_int64(len(x)), C.c_int(x.shape[1]), _p(centroids, _f32p),
+                                      C.c_int(len(centroids)), C.c_int(n_threads or num_threads()), _p(out, _i32p))
+    else:
+        port().oracle_ivf_assign(_p(x, _f32p), C.c_int64(len(x)), C.c_int(x.shape[1]), _p(centroids, _f32p),
+                                 C.c_int(len(centroids)), _p(out, _i32p))
     return out
 
 
@@ -247,14 +253,14 @@ def ivf_search(q, centroids, list_off, list_ids, list_vecs, nprobe, k, simd=Fals
     return D, I
 
 
-def kmeans(x, nlist, seed=4, iters=4):
+def kmeans(x, nlist, seed=4, iters=4, n_threads=0):
     x = np.ascontiguousarray(x, np.float32)
     rng = np.random.default_rng(seed)
     finite = np.flatnonzero(np.isfinite(x).all(axis=1))
     init = np.sort(rng.choice(finite, size=nlist, replace=False)).astype(np.int64)
     cent = np.empty((nlist, x.shape[1]), np.float32)
-    port().oracle_kmeans(_p(x, _f32p), C.c_int64(len(x)), C.c_int(x.shape[1]), C.c_int(nlist),
-                         _p(init, _i64p), C.c_int(iters), _p(cent, _f32p))
+    port().oracle_kmeans_fast(_p(x, _f32p), C.c_int64(len(x)), C.c_int(x.shape[1]), C.c_int(nlist),
+                              _p(init, _i64p), C.c_int(iters), C.c_int(n_threads or num_threads()), _p(cent, _f32p))
     return cent
 
 
