@@ -743,7 +743,7 @@ void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nl
     SOLO_REQUIRE(nlist > 0 && nlist <= IVF_MAX_NLIST, SOLO_EINVAL, "nlist must be in [1, %d] (got %d)", IVF_MAX_NLIST,
                  nlist);
     SOLO_REQUIRE(dim > 0 && dim <= 1536, SOLO_EINVAL, "dim must be in [1, 1536] (got %d)", dim);
-    SOLO_REQUIRE(ix.ntotal == 0, SOLO_ESTATE, "centroids cannot change while the index holds vectors; reset first");
+    ivf_reset(ix);  // new centroids define a new index: stored vectors are dropped
     ix.nlist = nlist;
     ix.dim = dim;
     size_t nb = (size_t)nlist * dim;

@@ -190,12 +190,17 @@ def run_solo(args, wl, rank, world, local_rank):
             eng.profile_enable(True)
         launches0 = eng.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ncu = profile and os.environ.get("SOLO_NCU") == "1"  # ncu --profile-from-start off
         with ClockSampler(local_rank) as clk:
+            if ncu:
+                torch.cuda.profiler.start()
             e0.record()
             for _ in range(steps):
                 step_fn()
             e1.record()
             barrier()
+            if ncu:
+                torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         prof = eng.profile() if profile else None
         eng.profile_enable(False)
