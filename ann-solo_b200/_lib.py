@@ -37,6 +37,7 @@ SYMBOLS = {
     "solo_last_error": (C.c_char_p, [_vp]),
     "solo_version": (C.c_char_p, []),
     "solo_set_stream": (C.c_int, [_vp, _vp]),
+    "solo_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "solo_synchronize": (C.c_int, [_vp]),
     "solo_set_vectorizer": (C.c_int, [_vp, _f64, _f64, _f64, C.c_int]),
     "solo_vectorize": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, C.c_int, _vp]),
@@ -52,6 +53,7 @@ SYMBOLS = {
     "solo_ivf_ntotal": (C.c_int, [_vp, C.c_int, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32)]),
     "solo_ivf_get_assignment": (C.c_int, [_vp, C.c_int, _vp]),
     "solo_ivf_search": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "solo_debug_scan_dump": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_i32), _vp, _vp]),
     "solo_ivf_coarse": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "solo_best_match_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _f64, C.c_int,
                                         C.c_int, _vp, _vp, _vp, _vp]),

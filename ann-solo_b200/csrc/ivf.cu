@@ -161,7 +161,8 @@ __device__ void block_bitonic_desc_u64(unsigned long long *a, int n) {
 // ======================================================================= dense -> sparse rows
 
 __global__ void dense_count_kernel(const float *__restrict__ x, int64_t n, int d, int32_t *__restrict__ nnz,
-                                   uint8_t *__restrict__ bad, int32_t *__restrict__ stats, int stat_base) {
+                                   uint8_t *__restrict__ bad, int32_t *__restrict__ stats, int stat_base,
+                                   float *__restrict__ row_norm) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -186,6 +187,7 @@ __global__ void dense_count_kernel(const float *__restrict__ x, int64_t n, int d
     if (lane == 0) {
         nnz[row] = isbad ? 0 : cnt;
         bad[row] = isbad ? 1 : 0;
+        if (row_norm) row_norm[row] = isbad ? 0.f : sqrtf(ss);
         if (!isbad) {
             if (neg) atomicOr(&stats[stat_base], 1);
             atomicMax(&stats[stat_base + 1], __float_as_int(sqrtf(ss)));
@@ -508,12 +510,28 @@ __global__ void __launch_bounds__(EN_WARPS * 32) scan_exact_kernel(ScanArgs a) {
 
 constexpr int TK_THREADS = 1024;
 
+// Error bound of the approximate (fp16 tensor-core) scores against the oracle's fp32 fmaf chain:
+// |approx - exact| <= eps. rel == 0 means the scan engine was exact. With non-negative data the
+// bound is relative to the score itself (sum |q_d c_d| equals the dot product); otherwise it is
+// relative to ||q|| * max ||c||. See DESIGN.md "Exact top-k out of tensor cores".
+struct EpsArgs {
+    float rel;
+    int nonneg;
+    const float *qnorm;  // [nq] L2 norms of the queries
+    float max_norm;      // max L2 norm of the stored vectors
+};
+__device__ __forceinline__ float band_eps(const EpsArgs &ea, float t, int q) {
+    if (ea.rel <= 0.f) return 0.f;
+    if (ea.nonneg) return ea.rel * fmaxf(t, 0.f) / (1.f - 2.f * ea.rel) + 4e-6f;
+    return ea.rel * ea.qnorm[q] * ea.max_norm + 4e-6f;
+}
+
 // After round 0: tau[q] = k-th best score so far (or -inf), buffer compacted to scores >= tau - margin.
 // retry != 0: used after an overflow — recompute tau from the (full) buffer, keep only the
 // round-0 part [0, n0) that still passes, mark non-overflowed queries done (tau = +inf).
 __global__ void __launch_bounds__(TK_THREADS)
 threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt, int32_t *__restrict__ n0,
-                 float *__restrict__ tau, int cap, int k, float rel_eps, int retry) {
+                 float *__restrict__ tau, int cap, int k, EpsArgs ea, int retry) {
     extern __shared__ uint32_t s_keys[];  // [cap]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_bc[4];
@@ -541,7 +559,8 @@ threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt
     int gt;
     const uint32_t T = block_kth_largest_u32(s_keys, n, k, false, 0u, s_hist, s_bc, &gt);
     const float t = ivf_o2f(T);
-    const float thr = t - 2.f * rel_eps * fabsf(t) - (rel_eps > 0.f ? 2e-6f : 0.f);
+    // every member of the exact top-k has approx >= (final approx k-th) - 2 eps >= t - 2 eps
+    const float thr = t - 2.f * band_eps(ea, t, q);
     const int limit = retry ? n0[q] : n;  // retry: only round-0 entries survive
     // compaction through registers (each thread owns a strided subset; two-phase to stay in place)
     unsigned long long keep[32];
@@ -582,14 +601,49 @@ struct FinalArgs {
     int charge;
     double tol;
     int tol_mode;          // -1: no mask
+    // exact re-scoring of the band around the k-th approximate score (tensor-core engine)
+    EpsArgs eps;
+    const float *q;        // (nq, d) fp32 queries
+    int d;
+    const int64_t *sp_off; // list-ordered sparse rows
+    const uint16_t *sp_idx;
+    const float *sp_val;
 };
 
+// exact score of list position `pos` against the query held in shared memory: the oracle's
+// sequential fp32 fmaf over ascending dimensions (zeros of the stored row skipped)
+__device__ __forceinline__ float exact_score(const FinalArgs &a, const float *s_q, uint32_t pos) {
+    float acc = 0.f;
+    const int64_t b = a.sp_off[pos], e = a.sp_off[pos + 1];
+    for (int64_t t = b; t < e; ++t) acc = __fmaf_rn(s_q[a.sp_idx[t]], a.sp_val[t], acc);
+    return acc;
+}
+
+__device__ __forceinline__ bool window_pass(const FinalArgs &a, int q, int id) {
+    if (a.tol_mode < 0) return true;
+    const double qm = a.q_prec_mz[q];
+    const double lm = (double)a.lib_prec_mz32[id];
+    bool ok;
+    // spectral_library.py:421-427, numexpr evaluates in float64
+    if (a.tol_mode == SOLO_TOL_DA) ok = __dmul_rn(fabs(__dsub_rn(qm, lm)), (double)a.charge) <= a.tol;
+    else ok = __dmul_rn(__ddiv_rn(fabs(__dsub_rn(qm, lm)), lm), 1000000.0) <= a.tol;
+    return ok && a.lib_valid[id];  // spectral_library.py:453
+}
+
+// K4: per query, the exact top-k (score desc, id asc) of everything the scan appended.
+//  1. T = k-th largest APPROXIMATE score; eps = error bound at T.
+//  2. entries above T + 2 eps are certainly in, entries below T - 2 eps certainly out; the band in
+//     between is re-scored EXACTLY (sorted-output mode re-scores everything that can be in, because
+//     it returns exact scores D).
+//  3. the remaining slots are filled with the best band entries under (exact score desc, id asc).
+// With an exact scan engine (eps.rel == 0) step 2 is the identity.
 __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
-    extern __shared__ uint32_t s_keys[];  // [cap] score keys, later id keys for ties
+    extern __shared__ uint32_t s_keys[];  // [cap] decision keys; s_q follows
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_bc[4];
-    __shared__ int s_nout;
+    __shared__ int s_nout, s_neq;
     __shared__ unsigned long long s_sorted[IVF_MAX_K];
+    float *s_q = reinterpret_cast<float *>(s_keys + a.cap);
     const int q = blockIdx.x;
     const unsigned long long *b = a.buf + (int64_t)q * a.cap;
     const int raw = a.cnt[q];
@@ -599,67 +653,74 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     }
     const int n = raw;
     const int kk = min(a.k, n);
-    if (threadIdx.x == 0) s_nout = 0;
+    const bool sorted_out = a.I != nullptr;
+    if (threadIdx.x == 0) {
+        s_nout = 0;
+        s_neq = 0;
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(b[i] >> 32)));
     __syncthreads();
-    uint32_t T = 0, Tid = 0;
-    int gt = 0;
     if (kk > 0) {
-        T = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt);
+        int gt;
+        if (a.eps.rel > 0.f) {
+            const uint32_t T = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt);
+            const float t = ivf_o2f(T);
+            const float e2 = 2.f * band_eps(a.eps, t, q);
+            const float lo = t - e2, hi = t + e2;
+            for (int j = threadIdx.x; j < a.d; j += blockDim.x) s_q[j] = a.q[(int64_t)q * a.d + j];
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long e = b[i];
+                const float s = __uint_as_float((uint32_t)(e >> 32));
+                uint32_t key;
+                if (s < lo) key = 0u;                                  // certainly out
+                else if (s > hi && !sorted_out) key = 0xFFFFFFFFu;     // certainly in
+                else key = ivf_f2o(exact_score(a, s_q, (uint32_t)(e & 0xFFFFFFFFull)));
+                s_keys[i] = key;
+            }
+            __syncthreads();
+        }
+        // exact selection on the decision keys (0 = out)
+        const uint32_t T2 = block_kth_largest_u32(s_keys, n, kk, true, 0u, s_hist, s_bc, &gt);
         const int need_eq = kk - gt;
-        // ties at the threshold: keep the need_eq lowest ids. Re-key: tie entries -> ~id + 1 (non-zero), others -> 0.
         int n_eq_local = 0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) n_eq_local += (s_keys[i] == T);
-        // (count only to skip the second select when there is exactly one tie candidate per need)
-        __syncthreads();
-        __shared__ int s_neq;
-        if (threadIdx.x == 0) s_neq = 0;
-        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = s_keys[i];
+            n_eq_local += (key == T2);
+            if (key > T2) {  // strictly better than the k-th: in
+                const unsigned long long e = b[i];
+                const int id = a.list_ids[(uint32_t)(e & 0xFFFFFFFFull)];
+                if (sorted_out) {
+                    int slot = atomicAdd(&s_nout, 1);
+                    s_sorted[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+                } else if (window_pass(a, q, id)) {
+                    int slot = atomicAdd(&s_nout, 1);
+                    a.sel_ids[(int64_t)q * a.k + slot] = id;
+                }
+            }
+        }
         if (n_eq_local) atomicAdd(&s_neq, n_eq_local);
         __syncthreads();
         const int neq = s_neq;
-        if (neq > need_eq) {
-            // mark: winners by score get key 0xFFFFFFFF, losers 0, ties ~id
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                uint32_t key = s_keys[i];
-                if (key > T) s_keys[i] = 0xFFFFFFFFu;
-                else if (key < T) s_keys[i] = 0u;
-                else s_keys[i] = 0xFFFFFFFEu - (uint32_t)a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)];
-            }
-            __syncthreads();
-            int gt2;
-            // k-th largest over all keys: gt winners come first, then ties by ascending id
-            Tid = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt2);
-        } else {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                uint32_t key = s_keys[i];
-                s_keys[i] = key >= T ? 0xFFFFFFFFu : 0u;
-            }
-            Tid = 0xFFFFFFFFu;
-            __syncthreads();
+        // ties at the k-th score: the need_eq lowest ids win
+        uint32_t Tid = 1u;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = s_keys[i];
+            s_keys[i] = (key == T2) ? 0xFFFFFFFEu - (uint32_t)a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)] : 0u;
         }
-    }
-    // emit
-    const bool sorted_out = a.I != nullptr;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (kk > 0 && s_keys[i] >= Tid && s_keys[i] != 0u) {
-            const unsigned long long e = b[i];
-            const int id = a.list_ids[(uint32_t)(e & 0xFFFFFFFFull)];
-            if (sorted_out) {
-                int slot = atomicAdd(&s_nout, 1);
-                s_sorted[slot] = ((unsigned long long)ivf_f2o(__uint_as_float((uint32_t)(e >> 32))) << 32) |
-                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
-            } else {
-                bool ok = true;
-                if (a.tol_mode >= 0) {
-                    const double qm = a.q_prec_mz[q];
-                    const double lm = (double)a.lib_prec_mz32[id];
-                    // spectral_library.py:421-427, numexpr evaluates in float64
-                    if (a.tol_mode == SOLO_TOL_DA) ok = __dmul_rn(fabs(__dsub_rn(qm, lm)), (double)a.charge) <= a.tol;
-                    else ok = __dmul_rn(__ddiv_rn(fabs(__dsub_rn(qm, lm)), lm), 1000000.0) <= a.tol;
-                    ok = ok && a.lib_valid[id];  // spectral_library.py:453
-                }
-                if (ok) {
+        __syncthreads();
+        if (neq > need_eq) {
+            int gt2;
+            Tid = block_kth_largest_u32(s_keys, n, need_eq, true, 0u, s_hist, s_bc, &gt2);
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = s_keys[i];
+            if (key != 0u && key >= Tid) {
+                const int id = (int)(0xFFFFFFFEu - key);
+                if (sorted_out) {
+                    int slot = atomicAdd(&s_nout, 1);
+                    s_sorted[slot] = ((unsigned long long)T2 << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+                } else if (window_pass(a, q, id)) {
                     int slot = atomicAdd(&s_nout, 1);
                     a.sel_ids[(int64_t)q * a.k + slot] = id;
                 }
@@ -687,6 +748,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
         }
     }
 }
+
 
 // ======================================================================= list-order build
 
@@ -781,7 +843,7 @@ static void append_sparse_rows(solo_handle *h, IvfIndex &ix, const float *d_x, i
     bad.ensure(n);
     int rows_per_block = 8;
     dense_count_kernel<<<div_up(n, rows_per_block), rows_per_block * 32, 0, h->stream>>>(
-        d_x, n, d, cnt.as<int32_t>(), bad.as<uint8_t>(), ix.stats.as<int32_t>(), 0);
+        d_x, n, d, cnt.as<int32_t>(), bad.as<uint8_t>(), ix.stats.as<int32_t>(), 0, nullptr);
     SOLO_CUDA(cudaGetLastError());
     ix.row_off.ensure_keep((ix.ntotal + n + 1) * sizeof(int64_t), (ix.ntotal + 1) * sizeof(int64_t), h->stream);
     if (ix.ntotal == 0) SOLO_CUDA(cudaMemsetAsync(ix.row_off.p, 0, sizeof(int64_t), h->stream));
@@ -841,6 +903,18 @@ void ivf_finalize(solo_handle *h, IvfIndex &ix) {
     if (!ix.dirty) return;
     const int64_t n = ix.ntotal;
     const int nlist = ix.nlist;
+    {   // statistics gathered while rows were added: sign and largest norm decide the fp16 scale
+        int32_t st[4] = {0, 0, 0, 0};
+        SOLO_CUDA(cudaMemcpyAsync(st, ix.stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        if (st[0]) ix.nonneg = false;
+        memcpy(&ix.max_norm, &st[1], 4);
+        // fp16 copies hold x * 2^scale: keep |x| * 2^scale <= 2^15 and push small values away from
+        // the fp16 subnormal range (unit-norm rows: scale 10)
+        int s = 10;
+        if (ix.max_norm > 0.f) s = std::min(10, (int)std::floor(std::log2(32768.0 / (double)ix.max_norm)));
+        ix.scale_log2 = std::max(s, -14);
+    }
     std::vector<int32_t> row_list(n);
     if (n) {
         SOLO_CUDA(cudaMemcpyAsync(row_list.data(), ix.row_list.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -888,11 +962,8 @@ void ivf_finalize(solo_handle *h, IvfIndex &ix) {
     } else {
         SOLO_CUDA(cudaMemsetAsync(ix.sp_off.p, 0, sizeof(int64_t), h->stream));
     }
-    int32_t st[4] = {0, 0, 0, 0};
-    SOLO_CUDA(cudaMemcpyAsync(st, ix.stats.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
     SOLO_CUDA(cudaStreamSynchronize(h->stream));
-    if (st[0]) ix.nonneg = false;
-    memcpy(&ix.max_norm, &st[1], 4);
+    tc_make_tensor_map(ix);  // vec_h may have moved
     ix.dirty = false;
 }
 
@@ -906,8 +977,10 @@ static void sparsify_queries(solo_handle *h, IvfIndex &ix, const float *d_q, int
     DevBuf &qstats = h->scratch[3];
     qstats.ensure(4 * sizeof(int32_t));
     SOLO_CUDA(cudaMemsetAsync(qstats.p, 0, 4 * sizeof(int32_t), h->stream));
+    DevBuf &qnorm = h->scratch[22];
+    qnorm.ensure(std::max<size_t>((size_t)nq * sizeof(float), 16));
     dense_count_kernel<<<div_up(nq, 8), 256, 0, h->stream>>>(d_q, nq, ix.dim, cnt.as<int32_t>(), bad.as<uint8_t>(),
-                                                            qstats.as<int32_t>(), 0);
+                                                            qstats.as<int32_t>(), 0, qnorm.as<float>());
     SOLO_CUDA(cudaGetLastError());
     q_off.ensure((size_t)(nq + 1) * sizeof(int64_t));
     scan_counts(h, cnt.as<int32_t>(), nq, q_off.as<int64_t>(), 0);
@@ -1017,6 +1090,37 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     fill_f32_kernel<<<div_up(nq, 256), 256, 0, st>>>(tau.as<float>(), nq, -INFINITY);
     h->launches++;
 
+    // ---- scan engine: tcgen05 (fp16 inputs, fp32 accumulate, band re-rank) unless the dimension
+    // is not a multiple of 16 or SOLO_SCAN_ENGINE=exact asks for the CUDA-core engine (debugging)
+    static const bool env_exact = [] {
+        const char *e = getenv("SOLO_SCAN_ENGINE");
+        return e && strcmp(e, "exact") == 0;
+    }();
+    const bool use_tc = !env_exact && !h->opt_scan_exact && tc_scan_supported(ix) && ix.tmap_valid;
+    EpsArgs ea;
+    ea.rel = 0.f;
+    ea.nonneg = 0;
+    ea.qnorm = h->scratch[22].as<float>();
+    ea.max_norm = ix.max_norm;
+    int q_scale_log2 = 0;
+    DevBuf &qh = h->scratch[24], &tile_cnt = h->scratch[25], &tile_off = h->scratch[26];
+    if (use_tc) {
+        int32_t qst[4];
+        SOLO_CUDA(cudaMemcpyAsync(qst, h->scratch[3].p, sizeof qst, cudaMemcpyDeviceToHost, st));
+        SOLO_CUDA(cudaStreamSynchronize(st));
+        float qmax;
+        memcpy(&qmax, &qst[1], 4);
+        q_scale_log2 = 10;
+        if (qmax > 0.f) q_scale_log2 = std::max(-14, std::min(10, (int)std::floor(std::log2(32768.0 / (double)qmax))));
+        ea.rel = IVF_REL_EPS;
+        ea.nonneg = (ix.nonneg && qst[0] == 0) ? 1 : 0;
+        qh.ensure((size_t)nq * d * sizeof(__half));
+        f32_to_f16_scaled_kernel<<<div_up((int64_t)nq * d, 256), 256, 0, st>>>(a.q, (int64_t)nq * d, qh.as<__half>(),
+                                                                              ldexpf(1.f, q_scale_log2));
+        SOLO_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+
     ScanArgs sa;
     sa.gq = gq.as<int32_t>();
     sa.list_off = ix.list_off.as<int64_t>();
@@ -1032,7 +1136,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     const size_t en_smem = (size_t)EN_ENT * sizeof(uint2) + (EN_VCH + 4) * sizeof(int) + (size_t)EN_WARPS * d * sizeof(float);
     SOLO_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)en_smem));
     const int ysplit = std::max(1, std::min(64, div_up(kNumSMs * 8, nlist)));
-    const size_t tk_smem = (size_t)cap * sizeof(uint32_t);
+    const size_t tk_smem = (size_t)cap * sizeof(uint32_t) + (size_t)d * sizeof(float);
     SOLO_CUDA(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     // expected scanned vectors per query, for the flop figure of the stage
@@ -1041,14 +1145,19 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     auto run_round = [&](int round) {
         sa.goff = goff.as<int64_t>() + (size_t)round * nlist;
         StageTimer t(h, ST_SCAN, 1, round == 0 ? scan_units : 0.0);
-        scan_exact_kernel<<<dim3(nlist, ysplit), EN_WARPS * 32, en_smem, st>>>(sa);
-        SOLO_CUDA(cudaGetLastError());
+        if (use_tc) {
+            launch_scan_tc(h, ix, sa.goff, sa.gq, qh.as<__half>(), q_scale_log2, sa.tau, sa.buf, sa.cnt, cap, tile_cnt,
+                           tile_off);
+        } else {
+            scan_exact_kernel<<<dim3(nlist, ysplit), EN_WARPS * 32, en_smem, st>>>(sa);
+            SOLO_CUDA(cudaGetLastError());
+        }
     };
     run_round(0);
     {
         StageTimer t(h, ST_TOPK, 1);
         threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
-                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, 0.f, 0);
+                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, ea, 0);
         SOLO_CUDA(cudaGetLastError());
     }
     FinalArgs fa;
@@ -1064,6 +1173,12 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     fa.sel_ids = a.sel_ids;
     fa.sel_cnt = a.sel_cnt;
     fa.tol_mode = -1;
+    fa.eps = ea;
+    fa.q = a.q;
+    fa.d = d;
+    fa.sp_off = ix.sp_off.as<int64_t>();
+    fa.sp_idx = ix.sp_idx.as<uint16_t>();
+    fa.sp_val = ix.sp_val.as<float>();
     if (a.I == nullptr) {
         SOLO_REQUIRE(a.sel_ids && a.sel_cnt, SOLO_EINVAL, "no output requested");
         fa.q_prec_mz = a.win_q_prec_mz;
@@ -1090,7 +1205,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int32_t), st));
         StageTimer t(h, ST_TOPK, 1);
         threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
-                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, 0.f, 1);
+                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, ea, 1);
         SOLO_CUDA(cudaGetLastError());
     }
 }

@@ -231,6 +231,18 @@ int solo_set_stream(solo_handle *h, void *cuda_stream) {
     });
 }
 
+int solo_set_option(solo_handle *h, const char *key, int64_t value) {
+    if (!h || !key) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        if (strcmp(key, "scan_engine") == 0) {
+            SOLO_REQUIRE(value == 0 || value == 1, SOLO_EINVAL, "scan_engine must be 0 (tcgen05) or 1 (exact CUDA cores)");
+            h->opt_scan_exact = value == 1;
+        } else {
+            SOLO_REQUIRE(false, SOLO_EINVAL, "unknown option '%s'", key);
+        }
+    });
+}
+
 int solo_synchronize(solo_handle *h) {
     if (!h) return SOLO_EINVAL;
     return guarded(h, [&] { SOLO_CUDA(cudaStreamSynchronize(h->stream)); });
@@ -476,6 +488,30 @@ int solo_ivf_search(solo_handle *h, int charge, const float *queries, int nq, in
         SOLO_CUDA(cudaMemcpyAsync(I, dI.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
         if (D) SOLO_CUDA(cudaMemcpyAsync(D, dD.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int solo_debug_scan_dump(solo_handle *h, int charge, int nq, int32_t *cap, int32_t *counts, uint64_t *entries) {
+    if (!h || !cap) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        *cap = 32768;
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        if (counts) SOLO_CUDA(cudaMemcpy(counts, h->scratch[15].p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (entries) {
+            std::vector<int32_t> c(nq);
+            SOLO_CUDA(cudaMemcpy(c.data(), h->scratch[15].p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            std::vector<int32_t> ids(std::max<int64_t>(ix.nstored, 1));
+            SOLO_CUDA(cudaMemcpy(ids.data(), ix.list_ids.p, ix.nstored * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (int q = 0; q < nq; ++q) {
+                int n = std::min(c[q], 32768);
+                uint64_t *dst = entries + (size_t)q * 32768;
+                SOLO_CUDA(cudaMemcpy(dst, h->scratch[17].as<unsigned long long>() + (size_t)q * 32768,
+                                     (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < n; ++i)  // list position -> library row
+                    dst[i] = (dst[i] & 0xFFFFFFFF00000000ull) | (uint32_t)ids[(uint32_t)(dst[i] & 0xFFFFFFFFull)];
+            }
+        }
     });
 }
 

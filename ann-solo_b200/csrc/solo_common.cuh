@@ -155,6 +155,9 @@ struct IvfIndex {
     bool dirty = true;      // lists need rebuilding before the next search
     int64_t max_list_len = 0;
     int buf_cap = 0;        // per-query candidate buffer capacity used by the scan
+    // TMA descriptor (CUtensorMap, 128 bytes) of vec_h for the tcgen05 scan engine
+    alignas(64) unsigned char tmap_storage[128];
+    bool tmap_valid = false;
 };
 
 }  // namespace solo
@@ -166,6 +169,7 @@ struct solo_handle {
     std::string last_error;
     int64_t launches = 0;
     bool profile = false;
+    bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
     solo::StageProf prof[solo::ST_COUNT];
 
     // vectoriser
@@ -187,7 +191,7 @@ struct solo_handle {
     solo::DevBuf q_mz, q_mz_vec, q_int, q_off, q_prec_mz;
 
     // scratch
-    solo::DevBuf scratch[24];
+    solo::DevBuf scratch[32];
     // results of the last staged search
     solo::DevBuf r_best_row, r_best_score, r_n_pairs, r_pairs, r_n_cand, r_ovf;
     int r_nq = 0, r_max_pairs = 0;

@@ -61,6 +61,9 @@ class SoloEngine:
     def set_stream(self, cuda_stream: Optional[int]):
         self._check(self._lib.solo_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.solo_set_option(self._h, key.encode(), int(value)))
+
     def synchronize(self):
         self._check(self._lib.solo_synchronize(self._h))
 
@@ -152,6 +155,19 @@ class SoloEngine:
         self._check(self._lib.solo_ivf_search(self._h, int(charge), _ptr(q), nq, d, int(k), int(nprobe), _ptr(I),
                                               _ptr(D)))
         return D, I
+
+    def debug_scan_dump(self, charge: int, nq: int):
+        """Raw scan output of the last ivf_search: list of (scores f32, rows i64) per query."""
+        cap = C.c_int32()
+        counts = np.empty(nq, np.int32)
+        self._check(self._lib.solo_debug_scan_dump(self._h, int(charge), nq, C.byref(cap), _ptr(counts), None))
+        entries = np.zeros((nq, cap.value), np.uint64)
+        self._check(self._lib.solo_debug_scan_dump(self._h, int(charge), nq, C.byref(cap), _ptr(counts), _ptr(entries)))
+        out = []
+        for q in range(nq):
+            e = entries[q, :min(counts[q], cap.value)]
+            out.append(((e >> np.uint64(32)).astype(np.uint32).view(np.float32), (e & np.uint64(0xFFFFFFFF)).astype(np.int64)))
+        return counts, out
 
     def ivf_coarse(self, charge: int, queries: np.ndarray, nprobe: int) -> np.ndarray:
         q = _c(queries, np.float32)

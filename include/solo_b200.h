@@ -41,6 +41,9 @@ const char *solo_version(void);
 /* Run all work on an externally owned cudaStream_t (e.g. torch's current stream) so that
  * the caller's CUDA events bracket the kernels; NULL restores the handle's own stream. */
 int solo_set_stream(solo_handle *h, void *cuda_stream);
+/* Tuning/diagnostic switches. "scan_engine": 0 = tcgen05 tensor-core list scan with exact band
+ * re-rank (default), 1 = exact CUDA-core list scan (same results; used to cross-check). */
+int solo_set_option(solo_handle *h, const char *key, int64_t value);
 /* Block until all work queued by this handle is complete. */
 int solo_synchronize(solo_handle *h);
 
@@ -92,6 +95,11 @@ int solo_ivf_get_assignment(solo_handle *h, int charge, int32_t *list_of_row);
  * float32 descending (exact fp32 scores) padded with -inf; D may be NULL. */
 int solo_ivf_search(solo_handle *h, int charge, const float *queries, int nq, int dim, int k, int nprobe,
                     int64_t *I, float *D);
+/* Diagnostic: the candidate buffers the list scan of the LAST solo_ivf_search left behind —
+ * per query `counts[q]` entries of (float32 score bits << 32 | library row); *cap = row stride
+ * of `entries` in elements. With k >= everything scanned this exposes every raw scan score
+ * (approximate fp16-input scores for the tensor-core engine). */
+int solo_debug_scan_dump(solo_handle *h, int charge, int nq, int32_t *cap, int32_t *counts, uint64_t *entries);
 /* Coarse quantizer alone (IndexFlatIP.search on the centroids): probes (nq, nprobe) int32. */
 int solo_ivf_coarse(solo_handle *h, int charge, const float *queries, int nq, int dim, int nprobe,
                     int32_t *probes);
