@@ -158,6 +158,22 @@ __device__ void block_bitonic_desc_u64(unsigned long long *a, int n) {
     __syncthreads();
 }
 
+// Error bound of the approximate (fp16 tensor-core) scores against the oracle's fp32 fmaf chain:
+// |approx - exact| <= eps. rel == 0 means the scan engine was exact. With non-negative data the
+// bound is relative to the score itself (sum |q_d c_d| equals the dot product); otherwise it is
+// relative to ||q|| * max ||c||. See DESIGN.md "Exact top-k out of tensor cores".
+struct EpsArgs {
+    float rel;
+    int nonneg;
+    const float *qnorm;  // [nq] L2 norms of the queries
+    float max_norm;      // max L2 norm of the stored vectors
+};
+__device__ __forceinline__ float band_eps(const EpsArgs &ea, float t, int q) {
+    if (ea.rel <= 0.f) return 0.f;
+    if (ea.nonneg) return ea.rel * fmaxf(t, 0.f) / (1.f - 2.f * ea.rel) + 4e-6f;
+    return ea.rel * ea.qnorm[q] * ea.max_norm + 4e-6f;
+}
+
 // ======================================================================= dense -> sparse rows
 
 __global__ void dense_count_kernel(const float *__restrict__ x, int64_t n, int d, int32_t *__restrict__ nnz,
@@ -228,7 +244,7 @@ template <int MODE>
 __global__ void __launch_bounds__(CO_WARPS * 32)
 coarse_exact_kernel(const int64_t *__restrict__ r_off, const uint16_t *__restrict__ r_idx,
                     const float *__restrict__ r_val, int64_t row0, int64_t nrows, const float *__restrict__ cent,
-                    int nlist, int d, float *__restrict__ scores, unsigned long long *__restrict__ best) {
+                    int nlist, int d, float *__restrict__ scores, unsigned long long *__restrict__ best, int pitch) {
     extern __shared__ float s_c[];  // [d][CO_PAD]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = blockIdx.x * 32;
@@ -253,7 +269,7 @@ coarse_exact_kernel(const int64_t *__restrict__ r_off, const uint16_t *__restric
             }
         }
         if (MODE == 0) {
-            if (cmine < nlist) scores[(row0 + r) * nlist + cmine] = acc;
+            if (cmine < nlist) scores[(row0 + r) * pitch + cmine] = acc;
         } else {
             unsigned long long key = 0ull;
             if (cmine < nlist && acc == acc)
@@ -271,7 +287,7 @@ coarse_exact_kernel(const int64_t *__restrict__ r_off, const uint16_t *__restric
 template <int MODE>
 static void launch_coarse(solo_handle *h, const IvfIndex &ix, const int64_t *r_off, const uint16_t *r_idx,
                           const float *r_val, int64_t row0, int64_t nrows, float *scores,
-                          unsigned long long *best) {
+                          unsigned long long *best, int pitch = 0) {
     if (nrows <= 0) return;
     auto k = coarse_exact_kernel<MODE>;
     size_t smem = (size_t)ix.dim * CO_PAD * sizeof(float);
@@ -284,7 +300,7 @@ static void launch_coarse(solo_handle *h, const IvfIndex &ix, const int64_t *r_o
     ysplit = std::min(ysplit, 65535);
     dim3 grid(tiles, ysplit);
     k<<<grid, CO_WARPS * 32, smem, h->stream>>>(r_off, r_idx, r_val, row0, nrows, ix.cent.as<float>(), ix.nlist,
-                                                ix.dim, scores, best);
+                                                ix.dim, scores, best, pitch ? pitch : ix.nlist);
     SOLO_CUDA(cudaGetLastError());
 }
 
@@ -301,16 +317,37 @@ __global__ void decode_assign_kernel(const unsigned long long *__restrict__ best
 
 constexpr int SEL_THREADS = 1024;
 
-// one CTA per query; keys = ordered score; ties at the threshold resolved towards lower list id
-__global__ void __launch_bounds__(SEL_THREADS)
-select_probes_kernel(const float *__restrict__ scores, int nlist, int nprobe, int32_t *__restrict__ probes,
-                     unsigned long long *__restrict__ probe_keys) {
+// one CTA per query; keys = ordered score; ties at the threshold resolved towards lower list id.
+// With approximate (tensor-core) coarse scores (ea.rel > 0) the band around the nprobe-th score is
+// re-scored exactly — the oracle's sequential fmaf over the query's non-zeros in ascending
+// dimension — so the selected set is the exact one. `exact_all` re-scores everything that can be
+// selected (sorted probe output carries exact scores).
+struct SelectArgs {
+    const float *scores;   // (nq, pitch)
+    int pitch;
+    int nlist;
+    int nprobe;
+    int32_t *probes;                  // (nq, nprobe) or null
+    unsigned long long *probe_keys;   // (nq, nprobe) or null
+    EpsArgs eps;
+    int exact_all;
+    const int64_t *q_off;             // sparse queries
+    const uint16_t *q_idx;
+    const float *q_val;
+    const float *cent;                // (nlist, d) fp32
+    int d;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a) {
     extern __shared__ uint32_t s_keys[];  // [nlist]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_bc[4];
     __shared__ int s_cnt, s_eq_taken;
     const int q = blockIdx.x;
-    const float *row = scores + (int64_t)q * nlist;
+    const int nlist = a.nlist, nprobe = a.nprobe;
+    int32_t *probes = a.probes;
+    unsigned long long *probe_keys = a.probe_keys;
+    const float *row = a.scores + (int64_t)q * a.pitch;
     for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
         float s = row[i];
         s_keys[i] = (s == s) ? ivf_f2o(s) : 0u;  // NaN -> lowest key
@@ -321,7 +358,29 @@ select_probes_kernel(const float *__restrict__ scores, int nlist, int nprobe, in
     }
     __syncthreads();
     int gt;
-    const uint32_t T = block_kth_largest_u32(s_keys, nlist, nprobe, false, 0u, s_hist, s_bc, &gt);
+    uint32_t T = block_kth_largest_u32(s_keys, nlist, nprobe, false, 0u, s_hist, s_bc, &gt);
+    if (a.eps.rel > 0.f && T != 0u) {
+        const float t = ivf_o2f(T);
+        const float e2 = 2.f * band_eps(a.eps, t, q);
+        const float lo = t - e2, hi = t + e2;
+        const int64_t qb = a.q_off[q], qe = a.q_off[q + 1];
+        for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
+            const uint32_t k0 = s_keys[i];
+            const float s = ivf_o2f(k0);
+            uint32_t key;
+            if (k0 == 0u || s < lo) key = 0u;                        // certainly out
+            else if (s > hi && !a.exact_all) key = 0xFFFFFFFFu;      // certainly in
+            else {
+                const float *c = a.cent + (int64_t)i * a.d;
+                float acc = 0.f;
+                for (int64_t e = qb; e < qe; ++e) acc = __fmaf_rn(a.q_val[e], c[a.q_idx[e]], acc);
+                key = (acc == acc) ? ivf_f2o(acc) : 0u;
+            }
+            s_keys[i] = key;
+        }
+        __syncthreads();
+        T = block_kth_largest_u32(s_keys, nlist, nprobe, true, 0u, s_hist, s_bc, &gt);
+    }
     const int need_eq = nprobe - gt;
     // strictly greater: any order
     for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
@@ -509,22 +568,6 @@ __global__ void __launch_bounds__(EN_WARPS * 32) scan_exact_kernel(ScanArgs a) {
 // ======================================================================= K4: thresholds and top-k
 
 constexpr int TK_THREADS = 1024;
-
-// Error bound of the approximate (fp16 tensor-core) scores against the oracle's fp32 fmaf chain:
-// |approx - exact| <= eps. rel == 0 means the scan engine was exact. With non-negative data the
-// bound is relative to the score itself (sum |q_d c_d| equals the dot product); otherwise it is
-// relative to ||q|| * max ||c||. See DESIGN.md "Exact top-k out of tensor cores".
-struct EpsArgs {
-    float rel;
-    int nonneg;
-    const float *qnorm;  // [nq] L2 norms of the queries
-    float max_norm;      // max L2 norm of the stored vectors
-};
-__device__ __forceinline__ float band_eps(const EpsArgs &ea, float t, int q) {
-    if (ea.rel <= 0.f) return 0.f;
-    if (ea.nonneg) return ea.rel * fmaxf(t, 0.f) / (1.f - 2.f * ea.rel) + 4e-6f;
-    return ea.rel * ea.qnorm[q] * ea.max_norm + 4e-6f;
-}
 
 // After round 0: tau[q] = k-th best score so far (or -inf), buffer compacted to scores >= tau - margin.
 // retry != 0: used after an overflow — recompute tau from the (full) buffer, keep only the
@@ -827,12 +870,19 @@ void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nl
     }
     ix.cent_max_norm = (float)mx;
     ix.nonneg = !neg;
+    ix.cent_nonneg = !neg;
+    // fp16 copy holds c * 2^s: |c| * 2^s <= 2^15, small values pushed away from the subnormal range
+    ix.cent_scale_log2 = 10;
+    if (mx > 0) ix.cent_scale_log2 = std::max(-14, std::min(10, (int)std::floor(std::log2(32768.0 / mx))));
     f32_to_f16_scaled_kernel<<<div_up(nb, 256), 256, 0, h->stream>>>(ix.cent.as<float>(), (int64_t)nb,
-                                                                      ix.cent_h.as<__half>(), ldexpf(1.f, ix.scale_log2));
+                                                                      ix.cent_h.as<__half>(),
+                                                                      ldexpf(1.f, ix.cent_scale_log2));
     SOLO_CUDA(cudaGetLastError());
     h->launches++;
     ivf_reset(ix);
+    ix.coarse_items_nq = -1;
     SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    tc_make_centroid_map(ix);
 }
 
 // sparse-convert `n` dense device rows and append them to the row-ordered store; returns nothing,
@@ -1016,12 +1066,49 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         StageTimer t(h, ST_COARSE, 0);
         sparsify_queries(h, ix, a.q, nq, q_off, q_idx, q_val);
     }
+    // ---- engine choice: tcgen05 (fp16 inputs, fp32 accumulate, exact band re-rank) unless the
+    // dimension is not a multiple of 16 or the CUDA-core engine is asked for (cross-check/debugging)
+    static const bool env_exact = [] {
+        const char *e = getenv("SOLO_SCAN_ENGINE");
+        return e && strcmp(e, "exact") == 0;
+    }();
+    const bool want_tc = !env_exact && !h->opt_scan_exact && tc_scan_supported(ix);
+    const bool use_tc = want_tc && ix.tmap_valid;
+    const bool use_tc_coarse = want_tc && ix.tmap_cent_valid;
+    EpsArgs ea;
+    ea.rel = 0.f;
+    ea.nonneg = 0;
+    ea.qnorm = h->scratch[22].as<float>();
+    ea.max_norm = ix.max_norm;
+    int q_scale_log2 = 0;
+    bool q_nonneg = false;
+    DevBuf &qh = h->scratch[24], &tile_cnt = h->scratch[25], &tile_off = h->scratch[26], &items = h->scratch[27];
+    DevBuf &qmask = h->scratch[28];
+    if (use_tc || use_tc_coarse) {
+        StageTimer t(h, ST_COARSE, 0);
+        int32_t qst[4];
+        SOLO_CUDA(cudaMemcpyAsync(qst, h->scratch[3].p, sizeof qst, cudaMemcpyDeviceToHost, st));
+        SOLO_CUDA(cudaStreamSynchronize(st));
+        float qmax;
+        memcpy(&qmax, &qst[1], 4);
+        q_scale_log2 = 10;
+        if (qmax > 0.f) q_scale_log2 = std::max(-14, std::min(10, (int)std::floor(std::log2(32768.0 / (double)qmax))));
+        q_nonneg = qst[0] == 0;
+        qh.ensure((size_t)nq * d * sizeof(__half));
+        qmask.ensure((size_t)nq * 8 * sizeof(uint32_t));
+        tc_prepare_queries(h, ix, a.q, nq, q_scale_log2, qh.as<__half>(), qmask.as<uint32_t>());
+    }
+
     DevBuf &coarse = h->scratch[7];
-    coarse.ensure((size_t)nq * nlist * sizeof(float));
+    const int pitch = (nlist + 31) & ~31;
+    coarse.ensure((size_t)nq * pitch * sizeof(float));
     {
         StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
-        launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
-                         coarse.as<float>(), nullptr);
+        if (use_tc_coarse)
+            launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, coarse.as<float>(), pitch);
+        else
+            launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
+                             coarse.as<float>(), nullptr, pitch);
     }
     DevBuf &probes = h->scratch[8], &pkeys = h->scratch[9];
     probes.ensure((size_t)nq * nprobe * sizeof(int32_t));
@@ -1035,8 +1122,27 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
             pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
             d_keys = pkeys.as<unsigned long long>();
         }
-        select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(coarse.as<float>(), nlist, nprobe,
-                                                            a.sort_probes ? nullptr : d_probes, d_keys);
+        SelectArgs sel;
+        memset(&sel, 0, sizeof sel);
+        sel.scores = coarse.as<float>();
+        sel.pitch = pitch;
+        sel.nlist = nlist;
+        sel.nprobe = nprobe;
+        sel.probes = a.sort_probes ? nullptr : d_probes;
+        sel.probe_keys = d_keys;
+        sel.eps = ea;
+        if (use_tc_coarse) {
+            sel.eps.rel = IVF_REL_EPS;
+            sel.eps.nonneg = (ix.cent_nonneg && q_nonneg) ? 1 : 0;
+            sel.eps.max_norm = ix.cent_max_norm;
+        }
+        sel.exact_all = a.sort_probes ? 1 : 0;
+        sel.q_off = q_off.as<int64_t>();
+        sel.q_idx = q_idx.as<uint16_t>();
+        sel.q_val = q_val.as<float>();
+        sel.cent = ix.cent.as<float>();
+        sel.d = d;
+        select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(sel);
         SOLO_CUDA(cudaGetLastError());
         if (a.sort_probes) {
             SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
@@ -1090,35 +1196,9 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     fill_f32_kernel<<<div_up(nq, 256), 256, 0, st>>>(tau.as<float>(), nq, -INFINITY);
     h->launches++;
 
-    // ---- scan engine: tcgen05 (fp16 inputs, fp32 accumulate, band re-rank) unless the dimension
-    // is not a multiple of 16 or SOLO_SCAN_ENGINE=exact asks for the CUDA-core engine (debugging)
-    static const bool env_exact = [] {
-        const char *e = getenv("SOLO_SCAN_ENGINE");
-        return e && strcmp(e, "exact") == 0;
-    }();
-    const bool use_tc = !env_exact && !h->opt_scan_exact && tc_scan_supported(ix) && ix.tmap_valid;
-    EpsArgs ea;
-    ea.rel = 0.f;
-    ea.nonneg = 0;
-    ea.qnorm = h->scratch[22].as<float>();
-    ea.max_norm = ix.max_norm;
-    int q_scale_log2 = 0;
-    DevBuf &qh = h->scratch[24], &tile_cnt = h->scratch[25], &tile_off = h->scratch[26];
     if (use_tc) {
-        int32_t qst[4];
-        SOLO_CUDA(cudaMemcpyAsync(qst, h->scratch[3].p, sizeof qst, cudaMemcpyDeviceToHost, st));
-        SOLO_CUDA(cudaStreamSynchronize(st));
-        float qmax;
-        memcpy(&qmax, &qst[1], 4);
-        q_scale_log2 = 10;
-        if (qmax > 0.f) q_scale_log2 = std::max(-14, std::min(10, (int)std::floor(std::log2(32768.0 / (double)qmax))));
         ea.rel = IVF_REL_EPS;
-        ea.nonneg = (ix.nonneg && qst[0] == 0) ? 1 : 0;
-        qh.ensure((size_t)nq * d * sizeof(__half));
-        f32_to_f16_scaled_kernel<<<div_up((int64_t)nq * d, 256), 256, 0, st>>>(a.q, (int64_t)nq * d, qh.as<__half>(),
-                                                                              ldexpf(1.f, q_scale_log2));
-        SOLO_CUDA(cudaGetLastError());
-        h->launches++;
+        ea.nonneg = (ix.nonneg && q_nonneg) ? 1 : 0;
     }
 
     ScanArgs sa;
@@ -1146,8 +1226,8 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         sa.goff = goff.as<int64_t>() + (size_t)round * nlist;
         StageTimer t(h, ST_SCAN, 1, round == 0 ? scan_units : 0.0);
         if (use_tc) {
-            launch_scan_tc(h, ix, sa.goff, sa.gq, qh.as<__half>(), q_scale_log2, sa.tau, sa.buf, sa.cnt, cap, tile_cnt,
-                           tile_off);
+            launch_scan_tc(h, ix, sa.goff, sa.gq, qh.as<__half>(), qmask.as<uint32_t>(), q_scale_log2, sa.tau, sa.buf,
+                           sa.cnt, cap, tile_cnt, tile_off, items);
         } else {
             scan_exact_kernel<<<dim3(nlist, ysplit), EN_WARPS * 32, en_smem, st>>>(sa);
             SOLO_CUDA(cudaGetLastError());

@@ -61,9 +61,14 @@ void scan_counts_i32(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off
 // tcgen05 scan engine (ivf_tc.cu)
 bool tc_scan_supported(const IvfIndex &ix);
 void tc_make_tensor_map(IvfIndex &ix);
+void tc_make_centroid_map(IvfIndex &ix);
+void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int nq, int q_scale_log2,
+                      float *out, int ld);
+void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int nq, int q_scale_log2, __half *qh,
+                        uint32_t *qmask);
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
-                    int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt, int cap,
-                    DevBuf &tile_cnt, DevBuf &tile_off);
+                    const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
+                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items);
 void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nlist, int dim);
 void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n, bool assign = true);  // d_x on device
 void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist, int iters, uint64_t seed,

@@ -17,15 +17,15 @@
 
 namespace solo {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BN = 256;
-constexpr int TC_BK = 64;      // fp16 elements per k-block = 128 bytes = one swizzle atom row
-constexpr int TC_STAGES = 4;
-constexpr int TC_BOX = 64;     // rows per TMA box
+constexpr int TC_BM = 128;       // queries per accumulator tile (MMA M)
+constexpr int TC_BK = 64;        // fp16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int TC_STAGES = 4;     // A (query) stages
+constexpr int TC_BOX = 32;       // rows per TMA box
 constexpr int TC_A_BYTES = TC_BM * 128;
-constexpr int TC_B_BYTES = TC_BN * 128;
-constexpr int TC_LAG = 2;      // A-producer signal lag (cp.async groups in flight)
+constexpr int TC_MAX_KB = 24;    // dim <= 1536
+constexpr int TC_LAG = 2;        // A-producer signal lag (cp.async groups in flight)
 constexpr int TC_THREADS = 320;
+constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,8 +58,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// 16-byte asynchronous copy; src_bytes == 0 writes zeros without touching global memory
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -110,58 +111,73 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+// One work item = one chunk of <= NB consecutive vectors of an inverted list, scored against the
+// list's whole query group of this round.
+struct __align__(16) TcItem {
+    int32_t p0;   // first list position of the chunk
+    int32_t nv;   // vectors in the chunk (1..NB)
+    int32_t g0;   // offset of the list's query group in gq
+    int32_t G;    // queries in the group
+};
+
 struct TcScanArgs {
-    const int64_t *goff;      // [nlist+1] query-group offsets of this round
+    const TcItem *items;
+    const int64_t *item_off;  // [nlist+1]; item_off[nlist] = number of items
     const int32_t *gq;        // grouped query ids
-    const int64_t *tile_off;  // [nlist+1] exclusive scan of tiles per list
-    const int64_t *list_off;  // [nlist+1]
     const __half *qh;         // (nq, dim) fp16 scaled queries
+    const uint32_t *qmask;    // (nq, 8): bit kb of word c = 16-byte chunk c of k-block kb is non-zero
     int nlist;
     int dim;
+    int nb;                   // chunk capacity NB (multiple of 32)
     float inv_scale;          // 2^-(scale_index + scale_query)
     const float *tau;         // [nq]
     unsigned long long *buf;  // [nq][cap]
     int32_t *cnt;             // [nq]
     int cap;
+    float *dense_out;         // MODE 1: (nq, dense_ld) all scores, row = query (gq == null: identity)
+    int dense_ld;
 };
 
 struct __align__(8) TcBarriers {
-    unsigned long long full[TC_STAGES];
-    unsigned long long empty[TC_STAGES];
+    unsigned long long full_a[TC_STAGES];
+    unsigned long long empty_a[TC_STAGES];
+    unsigned long long full_b[TC_MAX_KB];
+    unsigned long long empty_b[TC_MAX_KB];
     unsigned long long tmem_full[2];
     unsigned long long tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
 
-__device__ __forceinline__ int find_list(const int64_t *tile_off, int nlist, int64_t tile) {
-    int lo = 0, hi = nlist - 1;  // largest l with tile_off[l] <= tile
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tile_off[mid] <= tile) lo = mid;
-        else hi = mid - 1;
-    }
-    return lo;
-}
-
+// Persistent, warp-specialised. Shared memory: [A stages][B: num_kb k-blocks x NB rows x 128 B][barriers].
+// The list chunk (B operand) stays resident while all query blocks of the item stream through the
+// A stages; its k-block slots are released one by one during the item's last query block so the
+// next item's vectors arrive behind the last reader.
+// MODE 0: list scan (threshold + append). MODE 1: dense output (coarse quantizer: the "list" is the
+// centroid table, the query group is every query).
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base: align by hand (1 KB of slack is allocated)
     unsigned char *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-    // [A stages][B stages][barriers]
+    const int num_kb = (a.dim + TC_BK - 1) / TC_BK;
+    const int b_kb_bytes = a.nb * 128;
     unsigned char *sA = tc_smem;
     unsigned char *sB = tc_smem + TC_STAGES * TC_A_BYTES;
-    TcBarriers *bars = reinterpret_cast<TcBarriers *>(sB + TC_STAGES * TC_B_BYTES);
+    TcBarriers *bars = reinterpret_cast<TcBarriers *>(sB + (size_t)num_kb * b_kb_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = a.tile_off[a.nlist];
-    const int num_kb = (a.dim + TC_BK - 1) / TC_BK;
+    const int n_items = (int)a.item_off[a.nlist];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&bars->full[s]), 128 + 1);  // 128 A-producer threads + the TMA thread
-            mbar_init(smem_u32(&bars->empty[s]), 1);       // tcgen05.commit
+            mbar_init(smem_u32(&bars->full_a[s]), 128);  // the 128 A-producer threads
+            mbar_init(smem_u32(&bars->empty_a[s]), 1);   // tcgen05.commit
+        }
+        for (int kb = 0; kb < TC_MAX_KB; ++kb) {
+            mbar_init(smem_u32(&bars->full_b[kb]), 1);   // TMA thread (expect_tx)
+            mbar_init(smem_u32(&bars->empty_b[kb]), 1);  // tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->tmem_full[b]), 1);   // tcgen05.commit
@@ -182,44 +198,49 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         // ================= epilogue: TMEM -> registers -> threshold -> append =================
         uint32_t unit = 0;
         const int row = warp * 32 + lane;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int l = find_list(a.tile_off, a.nlist, tile);
-            const int qb = (int)(tile - a.tile_off[l]);
-            const int64_t g0 = a.goff[l];
-            const int G = (int)(a.goff[l + 1] - g0);
-            const int64_t p0 = a.list_off[l];
-            const int len = (int)(a.list_off[l + 1] - p0);
-            const int gi = qb * TC_BM + row;
-            const int q = gi < G ? a.gq[g0 + gi] : -1;
-            const float thr = q >= 0 ? a.tau[q] : INFINITY;
-            unsigned long long *qbuf = q >= 0 ? a.buf + (int64_t)q * a.cap : nullptr;
-            for (int n0 = 0; n0 < len; n0 += TC_BN, ++unit) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const TcItem it = a.items[item];
+            const int nqb = (it.G + TC_BM - 1) / TC_BM;
+            for (int qb = 0; qb < nqb; ++qb, ++unit) {
+                const int gi = qb * TC_BM + row;
+                const int q = gi < it.G ? (a.gq ? a.gq[it.g0 + gi] : gi) : -1;
+                const float thr = (MODE == 0 && q >= 0) ? a.tau[q] : INFINITY;
+                unsigned long long *qbuf = (MODE == 0 && q >= 0) ? a.buf + (int64_t)q * a.cap : nullptr;
                 const int buf = unit & 1;
-                const int nt = min(TC_BN, len - n0);
                 mbar_wait(smem_u32(&bars->tmem_full[buf]), (unit >> 1) & 1);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TC_BN);
-                for (int c0 = 0; c0 < nt; c0 += 32) {
+                const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256);
+                for (int c0 = 0; c0 < it.nv; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(tbase + (uint32_t)c0, r);
                     tc_wait_ld();
-                    if (c0 + 32 >= nt) {  // last chunk of this accumulator: hand the buffer back
+                    if (c0 + 32 >= it.nv) {  // last chunk of this accumulator: hand the buffer back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
                     }
-                    if (q >= 0) {
+                    if (q < 0) continue;
+                    if (MODE == 1) {
+                        // the row pitch is a multiple of 32 floats and p0 + c0 a multiple of 32: aligned, in-row
+                        float4 *dst = reinterpret_cast<float4 *>(a.dense_out + (size_t)q * a.dense_ld + it.p0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            dst[j] = make_float4(__uint_as_float(r[4 * j]) * a.inv_scale,
+                                                 __uint_as_float(r[4 * j + 1]) * a.inv_scale,
+                                                 __uint_as_float(r[4 * j + 2]) * a.inv_scale,
+                                                 __uint_as_float(r[4 * j + 3]) * a.inv_scale);
+                    } else {
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float s = __uint_as_float(r[j]) * a.inv_scale;
                             r[j] = __float_as_uint(s);
-                            if (c0 + j < nt && s >= thr) mask |= 1u << j;
+                            if (c0 + j < it.nv && s >= thr) mask |= 1u << j;
                         }
                         if (mask) {
                             const int n = __popc(mask);
                             int slot = atomicAdd(&a.cnt[q], n);
-                            const uint32_t pbase = (uint32_t)(p0 + n0 + c0);
+                            const uint32_t pbase = (uint32_t)(it.p0 + c0);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if ((mask >> j) & 1u) {
@@ -234,54 +255,49 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
             }
         }
     } else if (warp == 4) {
-        // ================= TMA producer: list vectors (B operand) =================
+        // ================= TMA producer: the item's list vectors (B operand, resident) =================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int l = find_list(a.tile_off, a.nlist, tile);
-                const int64_t p0 = a.list_off[l];
-                const int len = (int)(a.list_off[l + 1] - p0);
-                for (int n0 = 0; n0 < len; n0 += TC_BN) {
-                    const int nt = min(TC_BN, len - n0);
-                    const int nbox = (nt + TC_BOX - 1) / TC_BOX;
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % TC_STAGES;
-                        mbar_wait(smem_u32(&bars->empty[s]), ((it / TC_STAGES) & 1) ^ 1);
-                        const uint32_t fb = smem_u32(&bars->full[s]);
-                        mbar_expect_tx(fb, (uint32_t)(nbox * TC_BOX * 128));
-                        for (int j = 0; j < nbox; ++j)
-                            tma_load_2d(smem_u32(sB + s * TC_B_BYTES + j * TC_BOX * 128), &tmap_vec, kb * TC_BK,
-                                        (int)(p0 + n0 + j * TC_BOX), fb);
-                    }
+            uint32_t n_local = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_local) {
+                const TcItem it = a.items[item];
+                const int nbox = (it.nv + TC_BOX - 1) / TC_BOX;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bars->empty_b[kb]), (n_local & 1) ^ 1);
+                    const uint32_t fb = smem_u32(&bars->full_b[kb]);
+                    mbar_expect_tx(fb, (uint32_t)(nbox * TC_BOX * 128));
+                    for (int j = 0; j < nbox; ++j)
+                        tma_load_2d(smem_u32(sB + (size_t)kb * b_kb_bytes + j * TC_BOX * 128), &tmap_vec, kb * TC_BK,
+                                    it.p0 + j * TC_BOX, fb);
                 }
             }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t it = 0, unit = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int l = find_list(a.tile_off, a.nlist, tile);
-                const int len = (int)(a.list_off[l + 1] - a.list_off[l]);
-                for (int n0 = 0; n0 < len; n0 += TC_BN, ++unit) {
+            uint32_t st = 0, unit = 0, n_local = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_local) {
+                const TcItem it = a.items[item];
+                const int nqb = (it.G + TC_BM - 1) / TC_BM;
+                const uint32_t idesc = make_idesc_f16((it.nv + 15) & ~15);
+                for (int qb = 0; qb < nqb; ++qb, ++unit) {
                     const int buf = unit & 1;
-                    const int nt = min(TC_BN, len - n0);
-                    const uint32_t idesc = make_idesc_f16((nt + 15) & ~15);
                     mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((unit >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BN);
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % TC_STAGES;
-                        mbar_wait(smem_u32(&bars->full[s]), (it / TC_STAGES) & 1);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+                    for (int kb = 0; kb < num_kb; ++kb, ++st) {
+                        const int s = st % TC_STAGES;
+                        if (qb == 0) mbar_wait(smem_u32(&bars->full_b[kb]), n_local & 1);
+                        mbar_wait(smem_u32(&bars->full_a[s]), (st / TC_STAGES) & 1);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(sA + s * TC_A_BYTES);
-                        const uint32_t b_addr = smem_u32(sB + s * TC_B_BYTES);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)kb * b_kb_bytes);
                         const int ksteps = min(TC_BK, a.dim - kb * TC_BK) / 16;
                         for (int k = 0; k < ksteps; ++k) {
                             tc_mma_f16(tmem_d, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
                                        (kb | k) != 0 ? 1u : 0u);
                         }
-                        tc_commit(smem_u32(&bars->empty[s]));  // frees the stage when these MMAs retire
+                        tc_commit(smem_u32(&bars->empty_a[s]));  // frees the A stage when these MMAs retire
+                        if (qb == nqb - 1) tc_commit(smem_u32(&bars->empty_b[kb]));  // last reader of this B slot
                     }
                     tc_commit(smem_u32(&bars->tmem_full[buf]));
                 }
@@ -292,38 +308,34 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         const int p = threadIdx.x - 6 * 32;  // 0..127
         const int chunk = p & 7;             // 16-byte chunk inside the 128-byte k-block row
         const int rbase = p >> 3;            // rows rbase, rbase+16, ..., rbase+112
-        uint32_t it = 0;
+        const uint32_t dst_off = (uint32_t)(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));
+        uint32_t st = 0;
         uint32_t pending[TC_LAG + 1];
         int npend = 0;
         const size_t row_bytes = (size_t)a.dim * sizeof(__half);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int l = find_list(a.tile_off, a.nlist, tile);
-            const int qb = (int)(tile - a.tile_off[l]);
-            const int64_t g0 = a.goff[l];
-            const int G = (int)(a.goff[l + 1] - g0);
-            const int len = (int)(a.list_off[l + 1] - a.list_off[l]);
-            const unsigned char *src[8];
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const TcItem it = a.items[item];
+            const int nqb = (it.G + TC_BM - 1) / TC_BM;
+            for (int qb = 0; qb < nqb; ++qb) {
+                const unsigned char *src[8];
+                uint32_t nz[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int gi = qb * TC_BM + rbase + 16 * i;
-                int q = a.gq[g0 + (gi < G ? gi : 0)];  // padding rows replay a valid query; the epilogue skips them
-                src[i] = reinterpret_cast<const unsigned char *>(a.qh) + (size_t)q * row_bytes + chunk * 16;
-            }
-            for (int n0 = 0; n0 < len; n0 += TC_BN) {
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    mbar_wait(smem_u32(&bars->empty[s]), ((it / TC_STAGES) & 1) ^ 1);
-                    const bool valid = kb * TC_BK + chunk * 8 < a.dim;  // last k-block may be partial
-                    if (valid) {
-                        const uint32_t dst0 = smem_u32(sA + s * TC_A_BYTES);
+                for (int i = 0; i < 8; ++i) {
+                    const int gi = qb * TC_BM + rbase + 16 * i;
+                    const bool real = gi < it.G;
+                    const int q = a.gq ? a.gq[it.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                    src[i] = reinterpret_cast<const unsigned char *>(a.qh) + (size_t)q * row_bytes + chunk * 16;
+                    nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;  // padding rows are zero-filled
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++st) {
+                    const int s = st % TC_STAGES;
+                    mbar_wait(smem_u32(&bars->empty_a[s]), ((st / TC_STAGES) & 1) ^ 1);
+                    const uint32_t dst0 = smem_u32(sA + s * TC_A_BYTES) + dst_off;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = rbase + 16 * i;
-                            cp_async16(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), src[i] + (size_t)kb * 128);
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        cp_async16_zfill(dst0 + i * 16 * 128, src[i] + (size_t)kb * 128, ((nz[i] >> kb) & 1u) ? 16u : 0u);
                     cp_async_commit();
-                    pending[npend++] = smem_u32(&bars->full[s]);
+                    pending[npend++] = smem_u32(&bars->full_a[s]);
                     if (npend > TC_LAG) {
                         cp_async_wait<TC_LAG>();
                         fence_proxy_async();
@@ -348,13 +360,62 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     }
 }
 
-__global__ void tc_tile_count_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off, int nlist,
-                                     int32_t *__restrict__ cnt) {
+__global__ void tc_item_count_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off, int nlist,
+                                     int nb, int32_t *__restrict__ cnt) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     int64_t G = goff[l + 1] - goff[l];
     int64_t len = list_off[l + 1] - list_off[l];
-    cnt[l] = (len > 0 && G > 0) ? (int32_t)((G + TC_BM - 1) / TC_BM) : 0;
+    cnt[l] = (len > 0 && G > 0) ? (int32_t)((len + nb - 1) / nb) : 0;
+}
+
+__global__ void tc_item_fill_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off,
+                                    const int64_t *__restrict__ item_off, int nlist, int nb, TcItem *__restrict__ items) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlist) return;
+    const int64_t o = item_off[l];
+    const int n = (int)(item_off[l + 1] - o);
+    const int64_t p0 = list_off[l];
+    const int len = (int)(list_off[l + 1] - p0);
+    for (int c = 0; c < n; ++c) {
+        TcItem it;
+        it.p0 = (int32_t)(p0 + (int64_t)c * nb);
+        it.nv = min(nb, len - c * nb);
+        it.g0 = (int32_t)goff[l];
+        it.G = (int32_t)(goff[l + 1] - goff[l]);
+        items[o + c] = it;
+    }
+}
+
+// fp32 queries -> scaled fp16 rows + per-(query, chunk) non-zero masks for the zero-fill gather.
+// One thread per (query, 16-byte chunk position c): it walks the k-blocks.
+__global__ void tc_prepare_queries_kernel(const float *__restrict__ x, int nq, int dim, float scale,
+                                          __half *__restrict__ y, uint32_t *__restrict__ qmask) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nq * 8) return;
+    const int q = (int)(t >> 3), c = (int)(t & 7);
+    const int num_kb = (dim + TC_BK - 1) / TC_BK;
+    uint32_t m = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+        const int d0 = kb * TC_BK + c * 8;
+        if (d0 >= dim) break;
+        const float *src = x + (int64_t)q * dim + d0;
+        __align__(16) __half hv[8];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = d0 + j < dim ? src[j] * scale : 0.f;
+            hv[j] = __float2half_rn(v);
+            any |= (__half_as_ushort(hv[j]) & 0x7FFFu) != 0;
+        }
+        if (d0 + 8 <= dim) {
+            *reinterpret_cast<uint4 *>(y + (int64_t)q * dim + d0) = *reinterpret_cast<const uint4 *>(hv);
+        } else {
+            for (int j = 0; d0 + j < dim; ++j) y[(int64_t)q * dim + d0 + j] = hv[j];
+        }
+        if (any) m |= 1u << kb;
+    }
+    qmask[t] = m;
 }
 
 // ---------------------------------------------------------------- host side
@@ -377,53 +438,141 @@ static PFN_encodeTiled get_encode_fn() {
 
 bool tc_scan_supported(const IvfIndex &ix) { return ix.dim % 16 == 0 && ix.dim >= 16; }
 
+static bool tc_encode_rows(void *storage, const void *base, int dim, int64_t rows) {
+    CUtensorMap *m = reinterpret_cast<CUtensorMap *>(storage);
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BOX};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SOLO_REQUIRE(r == CUDA_SUCCESS, SOLO_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return true;
+}
+
 // (re)build the TMA descriptor of the list-ordered fp16 vectors; called from ivf_finalize
 void tc_make_tensor_map(IvfIndex &ix) {
     ix.tmap_valid = false;
     if (!tc_scan_supported(ix) || ix.nstored == 0) return;
     static_assert(sizeof(CUtensorMap) <= sizeof(ix.tmap_storage), "tensor map storage too small");
-    CUtensorMap *m = reinterpret_cast<CUtensorMap *>(ix.tmap_storage);
-    cuuint64_t gdim[2] = {(cuuint64_t)ix.dim, (cuuint64_t)ix.nstored};
-    cuuint64_t gstr[1] = {(cuuint64_t)ix.dim * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BOX};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ix.vec_h.p, gdim, gstr, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SOLO_REQUIRE(r == CUDA_SUCCESS, SOLO_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    ix.tmap_valid = true;
+    ix.tmap_valid = tc_encode_rows(ix.tmap_storage, ix.vec_h.p, ix.dim, ix.nstored);
+}
+
+// the same for the fp16 centroid table; called from ivf_set_centroids
+void tc_make_centroid_map(IvfIndex &ix) {
+    ix.tmap_cent_valid = false;
+    if (!tc_scan_supported(ix) || ix.nlist == 0) return;
+    ix.tmap_cent_valid = tc_encode_rows(ix.tmap_cent_storage, ix.cent_h.p, ix.dim, ix.nlist);
+}
+
+// chunk capacity NB: the largest multiple of 32 (<= 256) whose resident B region fits next to the A stages
+static int tc_chunk_rows(const IvfIndex &ix) {
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64 - TC_STAGES * TC_A_BYTES;
+    int nb = avail / (num_kb * 128) / 32 * 32;
+    return std::min(nb, 256);
+}
+
+void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int nq, int q_scale_log2, __half *qh,
+                        uint32_t *qmask) {
+    const int64_t n = (int64_t)nq * 8;
+    tc_prepare_queries_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(q, nq, ix.dim, ldexpf(1.f, q_scale_log2), qh, qmask);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches++;
 }
 
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
-                    int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt, int cap,
-                    DevBuf &tile_cnt, DevBuf &tile_off) {
+                    const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
+                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
     SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
     const int nlist = ix.nlist;
-    tile_cnt.ensure((size_t)nlist * sizeof(int32_t));
-    tile_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
-    tc_tile_count_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(), nlist,
-                                                                    tile_cnt.as<int32_t>());
-    scan_counts_i32(h, tile_cnt.as<int32_t>(), nlist, tile_off.as<int64_t>());
+    const int nb = tc_chunk_rows(ix);
+    SOLO_REQUIRE(nb >= 32, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
+    item_cnt.ensure((size_t)nlist * sizeof(int32_t));
+    item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
+    // every list contributes at most ceil(len / nb) <= len / nb + 1 items
+    items.ensure((size_t)(ix.nstored / nb + nlist + 1) * sizeof(TcItem));
+    tc_item_count_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(), nlist, nb,
+                                                                    item_cnt.as<int32_t>());
+    scan_counts_i32(h, item_cnt.as<int32_t>(), nlist, item_off.as<int64_t>());
+    tc_item_fill_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(),
+                                                                   item_off.as<int64_t>(), nlist, nb, items.as<TcItem>());
     TcScanArgs a;
-    a.goff = goff;
+    a.items = items.as<TcItem>();
+    a.item_off = item_off.as<int64_t>();
     a.gq = gq;
-    a.tile_off = tile_off.as<int64_t>();
-    a.list_off = ix.list_off.as<int64_t>();
     a.qh = qh;
+    a.qmask = qmask;
     a.nlist = nlist;
     a.dim = ix.dim;
+    a.nb = nb;
     a.inv_scale = ldexpf(1.f, -(ix.scale_log2 + q_scale_log2));
     a.tau = tau;
     a.buf = buf;
     a.cnt = cnt;
     a.cap = cap;
-    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + sizeof(TcBarriers) + 1024;
-    SOLO_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.dense_out = nullptr;
+    a.dense_ld = 0;
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
+    SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
+    SOLO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap map;
     memcpy(&map, ix.tmap_storage, sizeof map);
-    scan_tc_kernel<<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
+    scan_tc_kernel<0><<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
     SOLO_CUDA(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 3;
+}
+
+// K2 on the tensor cores: approximate scores of every query against every centroid,
+// out[q * ld + c] (ld = nlist rounded up to 32). The centroid table is scanned like one inverted
+// list whose query group is the whole batch.
+void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int nq, int q_scale_log2,
+                      float *out, int ld) {
+    SOLO_REQUIRE(ix.tmap_cent_valid, SOLO_ESTATE, "centroid tensor map missing");
+    const int nb = tc_chunk_rows(ix);
+    SOLO_REQUIRE(nb >= 32, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
+    const int n_items = div_up(ix.nlist, nb);
+    if (ix.coarse_items_nq != nq) {  // descriptors are tiny: built on the host, [count pair | items], cached per nq
+        std::vector<unsigned char> hbuf(sizeof(int64_t) * 2 + (size_t)n_items * sizeof(TcItem));
+        int64_t *hoff = reinterpret_cast<int64_t *>(hbuf.data());
+        hoff[0] = 0;
+        hoff[1] = n_items;
+        TcItem *hit = reinterpret_cast<TcItem *>(hbuf.data() + 2 * sizeof(int64_t));
+        for (int i = 0; i < n_items; ++i) {
+            hit[i].p0 = i * nb;
+            hit[i].nv = std::min(nb, ix.nlist - i * nb);
+            hit[i].g0 = 0;
+            hit[i].G = nq;
+        }
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));  // earlier launches may still read the old descriptors
+        ix.coarse_items.ensure(hbuf.size());
+        SOLO_CUDA(cudaMemcpy(ix.coarse_items.p, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice));
+        ix.coarse_items_nq = nq;
+    }
+    DevBuf &items = ix.coarse_items;
+    TcScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.items = reinterpret_cast<const TcItem *>(items.as<unsigned char>() + 2 * sizeof(int64_t));
+    a.item_off = items.as<int64_t>();
+    a.gq = nullptr;
+    a.qh = qh;
+    a.qmask = qmask;
+    a.nlist = 1;
+    a.dim = ix.dim;
+    a.nb = nb;
+    a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
+    a.dense_out = out;
+    a.dense_ld = ld;
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
+    SOLO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUtensorMap map;
+    memcpy(&map, ix.tmap_cent_storage, sizeof map);
+    scan_tc_kernel<1><<<std::min(kNumSMs, n_items), TC_THREADS, smem, h->stream>>>(map, a);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 1;
 }
 
 }  // namespace solo

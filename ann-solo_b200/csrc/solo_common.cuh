@@ -133,6 +133,7 @@ struct IvfIndex {
     bool nonneg = true;     // every stored value and centroid value is >= 0
     float max_norm = 0.f;   // max L2 norm over stored rows
     float cent_max_norm = 0.f;
+    bool cent_nonneg = true;  // every centroid value is >= 0
     int scale_log2 = 10;    // fp16 copies hold x * 2^scale_log2
     // centroids
     DevBuf cent;            // (nlist, dim) fp32 row-major
@@ -158,6 +159,11 @@ struct IvfIndex {
     // TMA descriptor (CUtensorMap, 128 bytes) of vec_h for the tcgen05 scan engine
     alignas(64) unsigned char tmap_storage[128];
     bool tmap_valid = false;
+    alignas(64) unsigned char tmap_cent_storage[128];  // the same for cent_h (tensor-core coarse quantizer)
+    bool tmap_cent_valid = false;
+    int cent_scale_log2 = 10;  // cent_h holds centroid * 2^cent_scale_log2
+    DevBuf coarse_items;       // work items of the tensor-core coarse pass, valid for coarse_items_nq queries
+    int coarse_items_nq = -1;
 };
 
 }  // namespace solo
