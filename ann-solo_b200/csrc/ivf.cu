@@ -74,64 +74,113 @@ static void scan_counts(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *
 
 void scan_counts_i32(solo_handle *h, const int32_t *cnt, int64_t n, int64_t *off) { scan_counts(h, cnt, n, off, 0); }
 
-// k-th largest (k >= 1) of `n` 32-bit keys in shared memory, restricted to entries with
-// key != skip_key when use_skip. Every thread of the block must call it. On return *count_gt
-// holds the number of participating keys strictly greater than the result.
+constexpr int KTH_BINS = 2048;  // shared-memory histogram bins of block_kth_largest_u32
+constexpr int KTH_BC = 48;      // broadcast / warp-sum scratch words
+
+// k-th largest (k >= 1, k <= number of participating keys) of `n` 32-bit keys in shared memory,
+// restricted to entries with key != skip_key when use_skip. Every thread of the block must call
+// it (blockDim.x a multiple of 32, at most 1024). On return *count_gt holds the number of
+// participating keys strictly greater than the result.
+// Radix select, most significant digit first, 11 bits per pass, starting at the highest bit in
+// which the block's minimum and maximum differ: scores of one query share their upper bits, so
+// the first histogram is already well spread (few same-bin shared-memory atomics).
+// When k2 > 0 (k2 <= k), *front_key receives a key F (resolution: the first radix pass) such that at
+// least k2 participating keys are >= F — a cheap "roughly the k2 best" split.
 __device__ uint32_t block_kth_largest_u32(const uint32_t *keys, int n, int k, bool use_skip, uint32_t skip_key,
-                                          uint32_t *s_hist /*256*/, uint32_t *s_bc /*4*/, int *count_gt) {
-    uint32_t prefix = 0, mask = 0;
-    int kk = k;
-    int gt = 0;
-    for (int pass = 3; pass >= 0; --pass) {
-        const int shift = pass * 8;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+                                          uint32_t *s_hist /*KTH_BINS*/, uint32_t *s_bc /*KTH_BC*/, int *count_gt,
+                                          int k2 = 0, uint32_t *front_key = nullptr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        s_bc[4] = 0xFFFFFFFFu;
+        s_bc[5] = 0u;
+    }
+    __syncthreads();
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t key = keys[i];
+        if (use_skip && key == skip_key) continue;
+        mn = min(mn, key);
+        mx = max(mx, key);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) {
+        atomicMin(&s_bc[4], mn);
+        atomicMax(&s_bc[5], mx);
+    }
+    __syncthreads();
+    mn = s_bc[4];
+    mx = s_bc[5];
+    __syncthreads();
+    if (mn >= mx) {  // all participating keys equal (or none participates)
+        *count_gt = 0;
+        if (front_key) *front_key = mx;
+        return mx;
+    }
+    bool first_pass = true;
+    int top = 32 - __clz(mn ^ mx);  // unresolved low bits
+    uint32_t mask = top >= 32 ? 0u : ~((1u << top) - 1u);
+    uint32_t prefix = mx & mask;
+    int kk = k, gt = 0;
+    while (top > 0) {
+        const int w = min(11, top);
+        const int shift = top - w;
+        const int nb = 1 << w;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            uint32_t key = keys[i];
+            const uint32_t key = keys[i];
             if (use_skip && key == skip_key) continue;
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & (uint32_t)(nb - 1)], 1u);
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // lane L owns bins [8L, 8L+8); walk from the top bin down
-            const int lane = threadIdx.x;
-            uint32_t loc[8];
-            uint32_t sum = 0;
+        // thread t owns bins [t * per, (t + 1) * per); suffix sums over threads, highest bins first
+        const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int b0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (int b = 0; b < per; ++b)
+            if (b0 + b < nb) sum += s_hist[b0 + b];
+        uint32_t incl = sum;  // inclusive suffix sum within the warp
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                loc[b] = s_hist[lane * 8 + b];
-                sum += loc[b];
-            }
-            // suffix sum over lanes: above = total count in lanes > lane
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_down_sync(0xffffffffu, incl, o);
-                if (lane + o < 32) incl += y;
-            }
-            uint32_t above = incl - sum;
-            bool mine = (above < (uint32_t)kk) && (incl >= (uint32_t)kk);
-            if (mine) {
-                uint32_t cum = above;
-                int digit = 0;
-#pragma unroll
-                for (int b = 7; b >= 0; --b) {
-                    if (cum < (uint32_t)kk && cum + loc[b] >= (uint32_t)kk) {
-                        digit = lane * 8 + b;
-                        s_bc[0] = (uint32_t)digit;
-                        s_bc[1] = cum;  // participating keys with a larger digit at this level
-                    }
-                    cum += loc[b];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += y;
+        }
+        if (lane == 0) s_bc[8 + warp] = incl;  // warp total
+        __syncthreads();
+        uint32_t above = incl - sum;  // threads of this warp with higher bins
+        for (int w2 = warp + 1; w2 < nwarps; ++w2) above += s_bc[8 + w2];
+        if (above < (uint32_t)kk && above + sum >= (uint32_t)kk) {
+            uint32_t cum = above;
+            for (int b = per - 1; b >= 0; --b) {
+                if (b0 + b >= nb) continue;
+                const uint32_t c = s_hist[b0 + b];
+                if (cum < (uint32_t)kk && cum + c >= (uint32_t)kk) {
+                    s_bc[0] = (uint32_t)(b0 + b);
+                    s_bc[1] = cum;  // participating keys with a larger digit at this level
                 }
+                cum += c;
+            }
+        }
+        if (first_pass && k2 > 0 && above < (uint32_t)k2 && above + sum >= (uint32_t)k2) {
+            uint32_t cum = above;
+            for (int b = per - 1; b >= 0; --b) {
+                if (b0 + b >= nb) continue;
+                const uint32_t c = s_hist[b0 + b];
+                if (cum < (uint32_t)k2 && cum + c >= (uint32_t)k2) s_bc[2] = prefix | ((uint32_t)(b0 + b) << shift);
+                cum += c;
             }
         }
         __syncthreads();
-        uint32_t digit = s_bc[0];
-        uint32_t larger = s_bc[1];
+        if (first_pass && front_key) *front_key = k2 > 0 ? s_bc[2] : 0u;
+        first_pass = false;
+        const uint32_t digit = s_bc[0];
+        const uint32_t larger = s_bc[1];
         gt += (int)larger;
         kk -= (int)larger;
         prefix |= digit << shift;
-        mask |= 255u << shift;
+        mask |= (uint32_t)(nb - 1) << shift;
+        top = shift;
         __syncthreads();
     }
     *count_gt = gt;
@@ -316,6 +365,7 @@ __global__ void decode_assign_kernel(const unsigned long long *__restrict__ best
 // ======================================================================= probe selection
 
 constexpr int SEL_THREADS = 1024;
+constexpr int SEL_BCAP = 1024;  // band entries re-scored on chip by select_probes_kernel
 
 // one CTA per query; keys = ordered score; ties at the threshold resolved towards lower list id.
 // With approximate (tensor-core) coarse scores (ea.rel > 0) the band around the nprobe-th score is
@@ -336,13 +386,14 @@ struct SelectArgs {
     const float *q_val;
     const float *cent;                // (nlist, d) fp32
     int d;
+    int n_front;                      // fast path: roughly the n_front best lists are written first
 };
 
 __global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a) {
     extern __shared__ uint32_t s_keys[];  // [nlist]
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_bc[4];
-    __shared__ int s_cnt, s_eq_taken;
+    __shared__ uint32_t s_hist[KTH_BINS];
+    __shared__ uint32_t s_bc[KTH_BC];
+    __shared__ int s_cnt, s_eq_taken, s_back;
     const int q = blockIdx.x;
     const int nlist = a.nlist, nprobe = a.nprobe;
     int32_t *probes = a.probes;
@@ -355,10 +406,71 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a
     if (threadIdx.x == 0) {
         s_cnt = 0;
         s_eq_taken = 0;
+        s_back = 0;
     }
     __syncthreads();
     int gt;
-    uint32_t T = block_kth_largest_u32(s_keys, nlist, nprobe, false, 0u, s_hist, s_bc, &gt);
+    uint32_t fkey = 0u;
+    uint32_t T = block_kth_largest_u32(s_keys, nlist, nprobe, false, 0u, s_hist, s_bc, &gt,
+                                       min(a.n_front, nprobe), &fkey);
+    if (a.eps.rel > 0.f && T != 0u && !a.exact_all) {
+        // fast path: everything above the band is in; only the (small) band is re-scored exactly and
+        // ranked under (exact score desc, list id asc)
+        __shared__ int s_nband;
+        __shared__ uint32_t s_band_id[SEL_BCAP];
+        __shared__ unsigned long long s_band_key[SEL_BCAP];
+        const float t = ivf_o2f(T);
+        const float e2 = 2.f * band_eps(a.eps, t, q);
+        const float lo = t - e2, hi = t + e2;
+        const int64_t qb = a.q_off[q], qe = a.q_off[q + 1];
+        if (threadIdx.x == 0) s_nband = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
+            const uint32_t k0 = s_keys[i];
+            if (k0 == 0u) continue;
+            const float s = ivf_o2f(k0);
+            if (s > hi) {  // front: close lists first (they seed the scan's running threshold)
+                const int slot = (a.n_front <= 0 || k0 >= fkey) ? atomicAdd(&s_cnt, 1) : nprobe - 1 - atomicAdd(&s_back, 1);
+                probes[(int64_t)q * nprobe + slot] = i;
+            } else if (s >= lo) {
+                const int pos = atomicAdd(&s_nband, 1);
+                if (pos < SEL_BCAP) s_band_id[pos] = (uint32_t)i;
+            }
+        }
+        __syncthreads();
+        const int nband = s_nband, certain = s_cnt + s_back;
+        if (nband <= SEL_BCAP) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+            for (int b = warp; b < nband; b += nwarps) {
+                const uint32_t i = s_band_id[b];
+                const float *c = a.cent + (int64_t)i * a.d;
+                float acc = 0.f;
+                for (int64_t e0 = qb; e0 < qe; e0 += 32) {
+                    const int64_t e = e0 + lane;
+                    const float v = e < qe ? a.q_val[e] : 0.f;
+                    const float cv = e < qe ? c[a.q_idx[e]] : 0.f;
+                    const int cnt = (int)min((int64_t)32, qe - e0);
+                    for (int u = 0; u < cnt; ++u)
+                        acc = __fmaf_rn(__shfl_sync(0xffffffffu, v, u), __shfl_sync(0xffffffffu, cv, u), acc);
+                }
+                if (lane == 0)
+                    s_band_key[b] = ((unsigned long long)((acc == acc) ? ivf_f2o(acc) : 0u) << 32) |
+                                    (unsigned long long)(0xFFFFFFFFu - i);
+            }
+            __syncthreads();
+            const int need = nprobe - certain;
+            for (int b = threadIdx.x; b < nband; b += blockDim.x) {
+                const unsigned long long key = s_band_key[b];
+                int r = 0;
+                for (int b2 = 0; b2 < nband; ++b2) r += s_band_key[b2] > key;
+                if (r < need) probes[(int64_t)q * nprobe + (nprobe - 1 - atomicAdd(&s_back, 1))] = (int32_t)s_band_id[b];
+            }
+            return;
+        }
+        __syncthreads();  // band larger than the on-chip list: generic path below
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    }
     if (a.eps.rel > 0.f && T != 0u) {
         const float t = ivf_o2f(T);
         const float e2 = 2.f * band_eps(a.eps, t, q);
@@ -576,8 +688,8 @@ __global__ void __launch_bounds__(TK_THREADS)
 threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt, int32_t *__restrict__ n0,
                  float *__restrict__ tau, int cap, int k, EpsArgs ea, int retry) {
     extern __shared__ uint32_t s_keys[];  // [cap]
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_bc[4];
+    __shared__ uint32_t s_hist[KTH_BINS];
+    __shared__ uint32_t s_bc[KTH_BC];
     __shared__ int s_out;
     const int q = blockIdx.x;
     unsigned long long *b = buf + (int64_t)q * cap;
@@ -682,8 +794,8 @@ __device__ __forceinline__ bool window_pass(const FinalArgs &a, int q, int id) {
 // With an exact scan engine (eps.rel == 0) step 2 is the identity.
 __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     extern __shared__ uint32_t s_keys[];  // [cap] decision keys; s_q follows
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_bc[4];
+    __shared__ uint32_t s_hist[KTH_BINS];
+    __shared__ uint32_t s_bc[KTH_BC];
     __shared__ int s_nout, s_neq;
     __shared__ unsigned long long s_sorted[IVF_MAX_K];
     float *s_q = reinterpret_cast<float *>(s_keys + a.cap);
@@ -1142,6 +1254,10 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         sel.q_val = q_val.as<float>();
         sel.cent = ix.cent.as<float>();
         sel.d = d;
+        // lists that fit the unconditional first scan round (c0 scores, see below), with some slack
+        sel.n_front = (ix.nstored > 0 && h->opt_front_probes)
+                          ? (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, 3 * (int64_t)h->opt_round0_scores * nlist / (4 * ix.nstored)))
+                          : 0;
         select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(sel);
         SOLO_CUDA(cudaGetLastError());
         if (a.sort_probes) {
@@ -1160,10 +1276,10 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
 
     // ---- per-query candidate buffers
     const int cap = 32768;
-    const int64_t c0 = 12288;
-    SOLO_REQUIRE(ix.max_list_len <= c0, SOLO_ECAPACITY,
+    const int64_t c0 = std::max<int64_t>(h->opt_round0_scores, ix.max_list_len);  // at least one whole list
+    SOLO_REQUIRE(ix.max_list_len <= IVF_ROUND0_SCORES, SOLO_ECAPACITY,
                  "an inverted list holds %lld vectors; the scan buffer supports lists up to %lld (use more lists)",
-                 (long long)ix.max_list_len, (long long)c0);
+                 (long long)ix.max_list_len, (long long)IVF_ROUND0_SCORES);
     DevBuf &r0 = h->scratch[10], &gcnt = h->scratch[11], &goff = h->scratch[12], &gq = h->scratch[13];
     DevBuf &tau = h->scratch[14], &cnt = h->scratch[15], &n0 = h->scratch[16], &buf = h->scratch[17];
     DevBuf &ovf = h->scratch[18];

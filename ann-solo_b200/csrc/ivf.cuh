@@ -8,6 +8,7 @@ namespace solo {
 
 constexpr int IVF_MAX_K = 2048;        // top-k rows returned per query
 constexpr int IVF_MAX_NLIST = 32768;   // coarse scores of one query are selected in shared memory
+constexpr int64_t IVF_ROUND0_SCORES = 12288;  // scores per query appended unconditionally by scan round 0
 constexpr float IVF_REL_EPS = 1.25e-3f;  // bound on |approx - exact| / sum|q_d c_d| for the fp16 tensor path
 
 // composite selection key: larger is better; (score desc, id asc) is a strict total order

@@ -13,6 +13,9 @@
 // K4 (ivf.cu) re-scores the band around the k-th score exactly, so the top-k is bit-exact.
 #include <cuda.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "ivf.cuh"
 
 namespace solo {
@@ -23,8 +26,9 @@ constexpr int TC_STAGES = 4;     // A (query) stages
 constexpr int TC_BOX = 32;       // rows per TMA box
 constexpr int TC_A_BYTES = TC_BM * 128;
 constexpr int TC_MAX_KB = 24;    // dim <= 1536
-constexpr int TC_LAG = 2;        // A-producer signal lag (cp.async groups in flight)
-constexpr int TC_THREADS = 320;
+constexpr int TC_PRODUCERS = 128;  // A-producer threads (warps 6..)
+constexpr int TC_EPI_WARPS = 8;   // two sets of four: set s drains accumulator buffer s
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32 + TC_PRODUCERS;
 constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -52,6 +56,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// one probe of the barrier phase; the predicate can be consumed later (latency overlaps other issue work)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -61,6 +79,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 // 16-byte asynchronous copy; src_bytes == 0 writes zeros without touching global memory
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's arrival on `bar` is triggered when all its earlier cp.async copies have landed (the
+// barrier's expected count includes it: .noinc). No blocking wait in the producer, every stage can be in flight.
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -99,6 +122,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
 // leading byte offset (unused for swizzled K-major, set to 1), stride byte offset = 1024 B between
 // 8-row groups, descriptor version 1, layout type 2 (128-byte swizzle).
@@ -136,7 +172,20 @@ struct TcScanArgs {
     int cap;
     float *dense_out;         // MODE 1: (nq, dense_ld) all scores, row = query (gq == null: identity)
     int dense_ld;
+    unsigned long long *prof; // optional (SOLO_TC_PROF=1): per-CTA wait-cycle counters, 8 per CTA
+    int debug;                // timing experiments only (SOLO_TC_DEBUG): 1 = skip query copies, 2 = skip score handling
 };
+
+// wait on an mbarrier; when profiling, add the cycles spent to *acc
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool on, unsigned long long &acc) {
+    if (on) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += (unsigned long long)(clock64() - t0);
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 struct __align__(8) TcBarriers {
     unsigned long long full_a[TC_STAGES];
@@ -149,19 +198,56 @@ struct __align__(8) TcBarriers {
     uint32_t pad;
 };
 
+// Walks the (item, query block) tiles of one CTA; the next item's descriptor is fetched one item ahead.
+struct TileCursor {
+    const TcItem *items;
+    int n_items, stride;
+    int item, qb, nqb;
+    TcItem cur, nxt;
+    bool valid;
+    __device__ __forceinline__ void load_next() {
+        const int ni = item + stride;
+        if (ni < n_items) nxt = items[ni];
+    }
+    __device__ __forceinline__ void init(const TcItem *it, int n, int first, int step) {
+        items = it;
+        n_items = n;
+        stride = step;
+        item = first;
+        qb = 0;
+        valid = item < n_items;
+        if (valid) cur = items[item];
+        nqb = valid ? (cur.G + TC_BM - 1) / TC_BM : 0;
+        load_next();
+    }
+    __device__ __forceinline__ bool first_qb() const { return qb == 0; }
+    __device__ __forceinline__ bool last_qb() const { return qb == nqb - 1; }
+    __device__ __forceinline__ void advance() {
+        if (++qb < nqb) return;
+        qb = 0;
+        item += stride;
+        valid = item < n_items;
+        cur = nxt;
+        nqb = (cur.G + TC_BM - 1) / TC_BM;
+        if (valid) load_next();
+    }
+};
+
 // Persistent, warp-specialised. Shared memory: [A stages][B: num_kb k-blocks x NB rows x 128 B][barriers].
 // The list chunk (B operand) stays resident while all query blocks of the item stream through the
 // A stages; its k-block slots are released one by one during the item's last query block so the
 // next item's vectors arrive behind the last reader.
 // MODE 0: list scan (threshold + append). MODE 1: dense output (coarse quantizer: the "list" is the
 // centroid table, the query group is every query).
-template <int MODE>
+// NUM_KB > 0 fixes the number of k-blocks at compile time (dim 800 -> 13) so that the gather loop
+// unrolls into copies with immediate offsets; NUM_KB == 0 is the generic kernel.
+template <int MODE, int NUM_KB, int EPI, int FLAGS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base: align by hand (1 KB of slack is allocated)
     unsigned char *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-    const int num_kb = (a.dim + TC_BK - 1) / TC_BK;
+    const int num_kb = NUM_KB > 0 ? NUM_KB : (a.dim + TC_BK - 1) / TC_BK;
     const int b_kb_bytes = a.nb * 128;
     unsigned char *sA = tc_smem;
     unsigned char *sB = tc_smem + TC_STAGES * TC_A_BYTES;
@@ -169,11 +255,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = (int)a.item_off[a.nlist];
+    const bool prof_on = a.prof != nullptr;
+    unsigned long long pw0 = 0, pw1 = 0, pw2 = 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&bars->full_a[s]), 128);  // the 128 A-producer threads
-            mbar_init(smem_u32(&bars->empty_a[s]), 1);   // tcgen05.commit
+            mbar_init(smem_u32(&bars->full_a[s]), TC_PRODUCERS);  // the A-producer threads
+            mbar_init(smem_u32(&bars->empty_a[s]), 1);            // tcgen05.commit
         }
         for (int kb = 0; kb < TC_MAX_KB; ++kb) {
             mbar_init(smem_u32(&bars->full_b[kb]), 1);   // TMA thread (expect_tx)
@@ -185,7 +273,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {  // TMEM: 2 accumulator buffers x 256 fp32 columns
+    if (warp == TC_EPI_WARPS) {  // TMEM: 2 accumulator buffers x 256 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -194,22 +282,41 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < 4) {
+    if (warp < TC_EPI_WARPS) {
         // ================= epilogue: TMEM -> registers -> threshold -> append =================
-        uint32_t unit = 0;
-        const int row = warp * 32 + lane;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const TcItem it = a.items[item];
-            const int nqb = (it.G + TC_BM - 1) / TC_BM;
-            for (int qb = 0; qb < nqb; ++qb, ++unit) {
-                const int gi = qb * TC_BM + row;
-                const int q = gi < it.G ? (a.gq ? a.gq[it.g0 + gi] : gi) : -1;
-                const float thr = (MODE == 0 && q >= 0) ? a.tau[q] : INFINITY;
-                unsigned long long *qbuf = (MODE == 0 && q >= 0) ? a.buf + (int64_t)q * a.cap : nullptr;
-                const int buf = unit & 1;
-                mbar_wait(smem_u32(&bars->tmem_full[buf]), (unit >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256);
+        // Two sets of four warps; set s owns accumulator buffer s, i.e. every other tile, so each set
+        // has two tile periods for its global-memory round trips. Warp w reads TMEM lanes 32 (w % 4)..
+        const int set = warp >> 2;
+        uint32_t unit = (uint32_t)set;
+        const int row = (warp & 3) * 32 + lane;
+        const long long t_begin = prof_on ? clock64() : 0;
+        const float scale = 1.f / a.inv_scale;  // exact power of two
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x);
+        if (set == 1 && tc.valid) tc.advance();
+        // the row's query and threshold are fetched one (own) tile ahead
+        int q = -1;
+        float thr = INFINITY;
+        if (tc.valid) {
+            const int gi = tc.qb * TC_BM + row;
+            q = gi < tc.cur.G ? (a.gq ? a.gq[tc.cur.g0 + gi] : gi) : -1;
+            if (MODE == 0 && q >= 0) thr = a.tau[q] * scale;
+        }
+        while (tc.valid) {
+            const TcItem it = tc.cur;
+            TileCursor nx = tc;
+            nx.advance();
+            if (nx.valid) nx.advance();
+            int q_next = -1;
+            if (nx.valid) {
+                const int gi = nx.qb * TC_BM + row;
+                q_next = gi < nx.cur.G ? (a.gq ? a.gq[nx.cur.g0 + gi] : gi) : -1;
+            }
+            const int buf = set;
+            mbar_wait_prof(smem_u32(&bars->tmem_full[buf]), (unit >> 1) & 1, prof_on, pw0);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * 256);
+            if (MODE == 1) {
                 for (int c0 = 0; c0 < it.nv; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(tbase + (uint32_t)c0, r);
@@ -220,141 +327,256 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                         if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
                     }
                     if (q < 0) continue;
-                    if (MODE == 1) {
-                        // the row pitch is a multiple of 32 floats and p0 + c0 a multiple of 32: aligned, in-row
-                        float4 *dst = reinterpret_cast<float4 *>(a.dense_out + (size_t)q * a.dense_ld + it.p0 + c0);
+                    // the row pitch is a multiple of 32 floats and p0 + c0 a multiple of 32: aligned, in-row
+                    float4 *dst = reinterpret_cast<float4 *>(a.dense_out + (size_t)q * a.dense_ld + it.p0 + c0);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            dst[j] = make_float4(__uint_as_float(r[4 * j]) * a.inv_scale,
-                                                 __uint_as_float(r[4 * j + 1]) * a.inv_scale,
-                                                 __uint_as_float(r[4 * j + 2]) * a.inv_scale,
-                                                 __uint_as_float(r[4 * j + 3]) * a.inv_scale);
-                    } else {
-                        uint32_t mask = 0;
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(r[4 * j]) * a.inv_scale,
+                                             __uint_as_float(r[4 * j + 1]) * a.inv_scale,
+                                             __uint_as_float(r[4 * j + 2]) * a.inv_scale,
+                                             __uint_as_float(r[4 * j + 3]) * a.inv_scale);
+                }
+            } else {
+                // groups of up to 128 columns: read them all, release the accumulator, then one
+                // atomic reservation per group and the (rare) stores
+                for (int g0 = 0; g0 < it.nv; g0 += 32 * EPI) {
+                    uint32_t r[EPI][32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float s = __uint_as_float(r[j]) * a.inv_scale;
-                            r[j] = __float_as_uint(s);
-                            if (c0 + j < it.nv && s >= thr) mask |= 1u << j;
+                    for (int c = 0; c < EPI; ++c)
+                        if (g0 + 32 * c < it.nv) tc_ld32(tbase + (uint32_t)(g0 + 32 * c), r[c]);
+                    tc_wait_ld();
+                    if (g0 + 32 * EPI >= it.nv) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+                    }
+                    if (q < 0 || (a.debug & 2)) continue;
+                    uint32_t mask[EPI];
+                    int n = 0;
+#pragma unroll
+                    for (int c = 0; c < EPI; ++c) {
+                        mask[c] = 0;
+                        if (g0 + 32 * c < it.nv) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)  // thr is pre-scaled: raw accumulators are compared
+                                if (__uint_as_float(r[c][j]) >= thr) mask[c] |= 1u << j;
+                            const int left = it.nv - (g0 + 32 * c);  // valid columns in this chunk
+                            if (left < 32) mask[c] &= (1u << left) - 1u;
+                            n += __popc(mask[c]);
                         }
-                        if (mask) {
-                            const int n = __popc(mask);
-                            int slot = atomicAdd(&a.cnt[q], n);
-                            const uint32_t pbase = (uint32_t)(it.p0 + c0);
+                    }
+                    if (n) {
+                        int slot = atomicAdd(&a.cnt[q], n);
+                        unsigned long long *qbuf = a.buf + (int64_t)q * a.cap;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if ((mask >> j) & 1u) {
-                                    if (slot < a.cap)
-                                        qbuf[slot] = ((unsigned long long)r[j] << 32) | (unsigned long long)(pbase + j);
-                                    ++slot;
+                        for (int c = 0; c < EPI; ++c) {
+                            if (mask[c]) {
+                                const uint32_t pbase = (uint32_t)(it.p0 + g0 + 32 * c);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if ((mask[c] >> j) & 1u) {
+                                        if (slot < a.cap)
+                                            qbuf[slot] = ((unsigned long long)__float_as_uint(__uint_as_float(r[c][j]) * a.inv_scale) << 32) |
+                                                         (unsigned long long)(pbase + j);
+                                        ++slot;
+                                    }
                                 }
                             }
                         }
                     }
                 }
             }
+            q = q_next;
+            thr = (MODE == 0 && q >= 0) ? a.tau[q] * scale : INFINITY;  // lands while waiting for the next accumulator
+            tc = nx;
+            unit += 2;
         }
-    } else if (warp == 4) {
+        if (prof_on && threadIdx.x == 0) {
+            a.prof[blockIdx.x * 8 + 0] = pw0;                                          // epilogue: wait tmem_full
+            a.prof[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_begin);    // total
+        }
+    } else if (warp == TC_EPI_WARPS) {
         // ================= TMA producer: the item's list vectors (B operand, resident) =================
-        if (lane == 0) {
-            uint32_t n_local = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_local) {
-                const TcItem it = a.items[item];
-                const int nbox = (it.nv + TC_BOX - 1) / TC_BOX;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(smem_u32(&bars->empty_b[kb]), (n_local & 1) ^ 1);
+        // The whole warp walks the loop (uniform control flow), one elected lane issues the copies.
+        uint32_t n_local = 0;
+        TcItem it, nxt;
+        int item = blockIdx.x;
+        if (item < n_items) it = a.items[item];
+        for (; item < n_items; item += gridDim.x, ++n_local) {
+            if (item + (int)gridDim.x < n_items) nxt = a.items[item + gridDim.x];
+            const int nbox = (it.nv + TC_BOX - 1) / TC_BOX;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_prof(smem_u32(&bars->empty_b[kb]), (n_local & 1) ^ 1, prof_on, pw0);
+                if (elect_one()) {
                     const uint32_t fb = smem_u32(&bars->full_b[kb]);
                     mbar_expect_tx(fb, (uint32_t)(nbox * TC_BOX * 128));
                     for (int j = 0; j < nbox; ++j)
                         tma_load_2d(smem_u32(sB + (size_t)kb * b_kb_bytes + j * TC_BOX * 128), &tmap_vec, kb * TC_BK,
                                     it.p0 + j * TC_BOX, fb);
                 }
+                __syncwarp();
             }
+            it = nxt;
         }
-    } else if (warp == 5) {
+        if (prof_on && lane == 0) a.prof[blockIdx.x * 8 + 1] = pw0;  // TMA: wait empty_b
+    } else if (warp == TC_EPI_WARPS + 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t st = 0, unit = 0, n_local = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_local) {
-                const TcItem it = a.items[item];
-                const int nqb = (it.G + TC_BM - 1) / TC_BM;
-                const uint32_t idesc = make_idesc_f16((it.nv + 15) & ~15);
-                for (int qb = 0; qb < nqb; ++qb, ++unit) {
-                    const int buf = unit & 1;
-                    mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((unit >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
-                    for (int kb = 0; kb < num_kb; ++kb, ++st) {
-                        const int s = st % TC_STAGES;
-                        if (qb == 0) mbar_wait(smem_u32(&bars->full_b[kb]), n_local & 1);
-                        mbar_wait(smem_u32(&bars->full_a[s]), (st / TC_STAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + s * TC_A_BYTES);
-                        const uint32_t b_addr = smem_u32(sB + (size_t)kb * b_kb_bytes);
-                        const int ksteps = min(TC_BK, a.dim - kb * TC_BK) / 16;
-                        for (int k = 0; k < ksteps; ++k) {
-                            tc_mma_f16(tmem_d, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
+        // Uniform control flow for the whole warp; one elected lane issues tcgen05.mma / commit.
+        const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        static_assert((TC_STAGES & (TC_STAGES - 1)) == 0, "TC_STAGES must be a power of two");
+        uint32_t stage = 0, phase = 0, unit = 0, n_local = 0;
+        bool ready = false;  // outcome of the early probe of full_a[stage]
+        const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x);
+        while (tc.valid) {
+            const uint32_t idesc = make_idesc_f16((a.debug & 4) ? 48 : (a.debug & 8) ? 16 : (tc.cur.nv + 15) & ~15);
+            const int buf = unit & 1;
+            mbar_wait_prof(smem_u32(&bars->tmem_empty[buf]), ((unit >> 1) & 1) ^ 1, prof_on, pw0);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+            const bool first_qb = tc.first_qb(), last_qb = tc.last_qb();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb]), n_local & 1, prof_on, pw1);
+                if (!ready) mbar_wait_prof(smem_u32(&bars->full_a[stage]), phase, prof_on, pw2);
+                // probe the next stage's barrier now; the answer is needed one k-block later
+                const uint32_t nstage = (stage + 1) & (TC_STAGES - 1);
+                const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
+                const bool ready_next = mbar_try_wait(smem_u32(&bars->full_a[nstage]), nphase);
+                tc_fence_after();
+                if (elect_one()) {
+                    uint64_t adesc = desc_hi | (uint64_t)(((a_base + stage * TC_A_BYTES) >> 4) & 0x3FFFu);
+                    uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                    const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                    if (!(a.debug & 16)) {
+                        tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                        for (int k = 1; k < ksteps; ++k) {
+                            adesc += 2;  // 32 bytes (16 fp16 along K) inside the swizzle atom
+                            bdesc += 2;
+                            if (!(a.debug & 32)) tc_mma_f16(tmem_d, adesc, bdesc, idesc, 1u);
                         }
-                        tc_commit(smem_u32(&bars->empty_a[s]));  // frees the A stage when these MMAs retire
-                        if (qb == nqb - 1) tc_commit(smem_u32(&bars->empty_b[kb]));  // last reader of this B slot
                     }
-                    tc_commit(smem_u32(&bars->tmem_full[buf]));
+                    tc_commit(smem_u32(&bars->empty_a[stage]));  // frees the A stage when these MMAs retire
+                    if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb]));  // last reader of this B slot
+                    if (kb == num_kb - 1) tc_commit(smem_u32(&bars->tmem_full[buf]));
                 }
+                __syncwarp();
+                stage = nstage;
+                phase = nphase;
+                ready = ready_next;
             }
+            if (last_qb) ++n_local;
+            ++unit;
+            tc.advance();
+        }
+        if (prof_on && lane == 0) {
+            a.prof[blockIdx.x * 8 + 2] = pw0;  // MMA: wait tmem_empty
+            a.prof[blockIdx.x * 8 + 3] = pw1;  // MMA: wait full_b
+            a.prof[blockIdx.x * 8 + 4] = pw2;  // MMA: wait full_a
         }
     } else {
         // ================= A producers: gather 128 query rows per k-block =================
-        const int p = threadIdx.x - 6 * 32;  // 0..127
+        // Thread p copies 16-byte chunk `chunk` of rows rbase + TC_PROD_ROWS_STEP * i; a chunk whose
+        // eight fp16 values are all zero is zero-filled without touching L2. The rows' query ids and
+        // non-zero masks are fetched one tile ahead.
+        const int p = threadIdx.x - (TC_EPI_WARPS + 2) * 32;  // 0..TC_PRODUCERS-1
         const int chunk = p & 7;             // 16-byte chunk inside the 128-byte k-block row
-        const int rbase = p >> 3;            // rows rbase, rbase+16, ..., rbase+112
+        const int rbase = p >> 3;
+        constexpr int RSTEP = TC_PRODUCERS / 8;  // row step between a thread's rows
+        constexpr int NR = TC_BM / RSTEP;        // rows per thread
         const uint32_t dst_off = (uint32_t)(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));
-        uint32_t st = 0;
-        uint32_t pending[TC_LAG + 1];
-        int npend = 0;
+        const uint32_t a_base = smem_u32(sA);
+        uint32_t stage = 0, phase = 0;
         const size_t row_bytes = (size_t)a.dim * sizeof(__half);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const TcItem it = a.items[item];
-            const int nqb = (it.G + TC_BM - 1) / TC_BM;
-            for (int qb = 0; qb < nqb; ++qb) {
-                const unsigned char *src[8];
-                uint32_t nz[8];
+        const unsigned char *qh_c = reinterpret_cast<const unsigned char *>(a.qh) + chunk * 16;
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x);
+        const unsigned char *src[NR];
+        uint32_t nz[NR];
+        int qn[NR];
+        if (tc.valid) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int gi = qb * TC_BM + rbase + 16 * i;
-                    const bool real = gi < it.G;
-                    const int q = a.gq ? a.gq[it.g0 + (real ? gi : 0)] : (real ? gi : 0);
-                    src[i] = reinterpret_cast<const unsigned char *>(a.qh) + (size_t)q * row_bytes + chunk * 16;
-                    nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;  // padding rows are zero-filled
-                }
-                for (int kb = 0; kb < num_kb; ++kb, ++st) {
-                    const int s = st % TC_STAGES;
-                    mbar_wait(smem_u32(&bars->empty_a[s]), ((st / TC_STAGES) & 1) ^ 1);
-                    const uint32_t dst0 = smem_u32(sA + s * TC_A_BYTES) + dst_off;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        cp_async16_zfill(dst0 + i * 16 * 128, src[i] + (size_t)kb * 128, ((nz[i] >> kb) & 1u) ? 16u : 0u);
-                    cp_async_commit();
-                    pending[npend++] = smem_u32(&bars->full_a[s]);
-                    if (npend > TC_LAG) {
-                        cp_async_wait<TC_LAG>();
-                        fence_proxy_async();
-                        mbar_arrive(pending[0]);
-#pragma unroll
-                        for (int j = 0; j < TC_LAG; ++j) pending[j] = pending[j + 1];
-                        --npend;
-                    }
-                }
+            for (int i = 0; i < NR; ++i) {
+                const int gi = rbase + RSTEP * i;
+                const bool real = gi < tc.cur.G;
+                const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                src[i] = qh_c + (size_t)q * row_bytes;
+                nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;  // padding rows are zero-filled
             }
         }
+        while (tc.valid) {
+            TileCursor nx = tc;
+            nx.advance();
+            const unsigned char *src_n[NR];
+            uint32_t nz_n[NR];
+            if (!(FLAGS & 1)) {  // no prefetch: fetch this tile's rows now
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int gi = tc.qb * TC_BM + rbase + RSTEP * i;
+                    const bool real = gi < tc.cur.G;
+                    const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                    src[i] = qh_c + (size_t)q * row_bytes;
+                    nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;
+                }
+            }
+            auto produce = [&](int kb) {
+                if ((FLAGS & 1) && kb == 0 && nx.valid) {  // next tile's query ids
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int gi = nx.qb * TC_BM + rbase + RSTEP * i;
+                        const bool real = gi < nx.cur.G;
+                        const int q = a.gq ? a.gq[nx.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                        qn[i] = real ? q : -1 - q;  // negative: padding row (zero-filled)
+                    }
+                }
+                if ((FLAGS & 1) && kb == num_kb / 2 && nx.valid) {  // ... and its masks / row pointers
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const bool real = qn[i] >= 0;
+                        const int q = real ? qn[i] : -1 - qn[i];
+                        src_n[i] = qh_c + (size_t)q * row_bytes;
+                        nz_n[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;
+                    }
+                }
+                mbar_wait_prof(smem_u32(&bars->empty_a[stage]), phase ^ 1u, prof_on, pw0);
+                const uint32_t dst0 = a_base + stage * TC_A_BYTES + dst_off;
+                if (!(a.debug & 1)) {
+#pragma unroll
+                    for (int i = 0; i < NR; ++i)
+                        cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
+                }
+                cp_async_arrive_noinc(smem_u32(&bars->full_a[stage]));
+                if (++stage == TC_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            };
+            if (NUM_KB > 0) {
+#pragma unroll
+                for (int kb = 0; kb < NUM_KB; ++kb) produce(kb);
+            } else {
+                for (int kb = 0; kb < num_kb; ++kb) produce(kb);
+            }
+            if (FLAGS & 1) {
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    src[i] = src_n[i];
+                    nz[i] = nz_n[i];
+                }
+            }
+            tc = nx;
+        }
         cp_async_wait<0>();
-        fence_proxy_async();
-        for (int j = 0; j < npend; ++j) mbar_arrive(pending[j]);
+        if (prof_on && p == 0) {
+            a.prof[blockIdx.x * 8 + 5] = pw0;  // A producer: wait empty_a
+            a.prof[blockIdx.x * 8 + 6] = pw1;  // A producer: wait cp.async data
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_EPI_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
@@ -466,6 +688,41 @@ void tc_make_centroid_map(IvfIndex &ix) {
     ix.tmap_cent_valid = tc_encode_rows(ix.tmap_cent_storage, ix.cent_h.p, ix.dim, ix.nlist);
 }
 
+// SOLO_TC_PROF=1 (debugging): per-role wait-cycle counters of the scan kernel, printed to stderr after
+// every launch (synchronises the device around the launch)
+static unsigned long long *g_tc_prof = nullptr;
+static unsigned long long *tc_prof_buffer() {
+    static const bool on = [] {
+        const char *e = getenv("SOLO_TC_PROF");
+        return e && e[0] == '1';
+    }();
+    if (!on) return nullptr;
+    if (!g_tc_prof) cudaMalloc(&g_tc_prof, kNumSMs * 8 * sizeof(unsigned long long));
+    cudaDeviceSynchronize();
+    cudaMemset(g_tc_prof, 0, kNumSMs * 8 * sizeof(unsigned long long));
+    cudaDeviceSynchronize();
+    return g_tc_prof;
+}
+static void tc_prof_report(solo_handle *h, const char *what, int ctas) {
+    (void)h;
+    if (!g_tc_prof) return;
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> v(kNumSMs * 8);
+    cudaMemcpy(v.data(), g_tc_prof, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    static const char *names[8] = {"epi:tmem_full", "tma:empty_b", "mma:tmem_empty", "mma:full_b",
+                                   "mma:full_a",    "a:empty_a",   "a:cp.async",     "total"};
+    fprintf(stderr, "[tc_prof %s]", what);
+    for (int c = 0; c < 8; ++c) {
+        double sum = 0, mx = 0;
+        for (int b = 0; b < ctas; ++b) {
+            sum += (double)v[b * 8 + c];
+            mx = std::max(mx, (double)v[b * 8 + c]);
+        }
+        fprintf(stderr, " %s=%.0fk/%.0fk", names[c], sum / ctas / 1e3, mx / 1e3);
+    }
+    fprintf(stderr, " (mean/max kcycles per CTA)\n");
+}
+
 // chunk capacity NB: the largest multiple of 32 (<= 256) whose resident B region fits next to the A stages
 static int tc_chunk_rows(const IvfIndex &ix) {
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
@@ -514,15 +771,23 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     a.cap = cap;
     a.dense_out = nullptr;
     a.dense_ld = 0;
+    a.prof = tc_prof_buffer();
+    static const int v_debug = getenv("SOLO_TC_DEBUG") ? atoi(getenv("SOLO_TC_DEBUG")) : 0;
+    a.debug = v_debug;
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
     const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
     SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
-    SOLO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap map;
     memcpy(&map, ix.tmap_storage, sizeof map);
-    scan_tc_kernel<0><<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
+    static const int v_epi2 = getenv("SOLO_TC_EPI2") ? 1 : 0;
+    void (*kern)(const CUtensorMap, TcScanArgs) = nullptr;
+    if (num_kb == 13) kern = v_epi2 ? scan_tc_kernel<0, 13, 2, 3> : scan_tc_kernel<0, 13, 1, 3>;
+    else kern = scan_tc_kernel<0, 0, 1, 3>;
+    SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
     SOLO_CUDA(cudaGetLastError());
     h->launches += 3;
+    tc_prof_report(h, "scan", kNumSMs);
 }
 
 // K2 on the tensor cores: approximate scores of every query against every centroid,
@@ -565,14 +830,17 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
     a.dense_out = out;
     a.dense_ld = ld;
+    a.prof = tc_prof_buffer();
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
     const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
-    SOLO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap map;
     memcpy(&map, ix.tmap_cent_storage, sizeof map);
-    scan_tc_kernel<1><<<std::min(kNumSMs, n_items), TC_THREADS, smem, h->stream>>>(map, a);
+    auto kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 3> : scan_tc_kernel<1, 0, 1, 3>;
+    SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<std::min(kNumSMs, n_items), TC_THREADS, smem, h->stream>>>(map, a);
     SOLO_CUDA(cudaGetLastError());
     h->launches += 1;
+    tc_prof_report(h, "coarse", std::min(kNumSMs, n_items));
 }
 
 }  // namespace solo

@@ -237,6 +237,11 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
         if (strcmp(key, "scan_engine") == 0) {
             SOLO_REQUIRE(value == 0 || value == 1, SOLO_EINVAL, "scan_engine must be 0 (tcgen05) or 1 (exact CUDA cores)");
             h->opt_scan_exact = value == 1;
+        } else if (strcmp(key, "round0_scores") == 0) {
+            SOLO_REQUIRE(value >= 1024 && value <= 16384, SOLO_EINVAL, "round0_scores must be in [1024, 16384]");
+            h->opt_round0_scores = (int)value;
+        } else if (strcmp(key, "front_probes") == 0) {
+            h->opt_front_probes = value != 0;
         } else {
             SOLO_REQUIRE(false, SOLO_EINVAL, "unknown option '%s'", key);
         }

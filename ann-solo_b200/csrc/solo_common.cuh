@@ -176,6 +176,8 @@ struct solo_handle {
     int64_t launches = 0;
     bool profile = false;
     bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
+    int opt_round0_scores = 8192;   // scores per query appended unconditionally by the first scan round
+    bool opt_front_probes = true;   // probe selection writes the closest lists first
     solo::StageProf prof[solo::ST_COUNT];
 
     // vectoriser

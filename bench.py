@@ -121,6 +121,9 @@ def run_solo(args, wl, rank, world, local_rank):
     lib, per_charge, q_by_charge = make_data(wl, rank)
     eng = SoloEngine(local_rank)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    for kv in filter(None, os.environ.get("SOLO_OPT", "").split(",")):  # tuning switches, e.g. round0_scores=6144
+        key, val = kv.split("=")
+        eng.set_option(key, int(val))
     t0 = time.time()
     charges = sorted(q_by_charge)
     n_vec = {}
@@ -210,6 +213,38 @@ def run_solo(args, wl, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), prof, launches, clk.summary()
 
+    if os.environ.get("SOLO_BENCH_STATS") == "1":  # diagnostic: per-query scan buffer fill and candidate counts
+        import ctypes as C
+        for z in charges:
+            eng.select_slot(z)
+            eng.search_staged(z, params)
+            eng.synchronize()
+            nq = len(q_by_charge[z]["prec_mz"])
+            cap, cnt = C.c_int32(), np.empty(nq, np.int32)
+            eng._check(eng._lib.solo_debug_scan_dump(eng._h, int(z), nq, C.byref(cap), cnt.ctypes.data_as(C.c_void_p), None))
+            eng._staged_nq = nq
+            nc = eng.fetch_results()["n_cand"]
+            pc = np.percentile(cnt, [1, 50, 90, 99, 100]).astype(int).tolist()
+            log(f"stats z={z}: nq={nq} scan-buffer entries/query p1/p50/p90/p99/max = {pc} mean={cnt.mean():.0f}; "
+                f"scored candidates/query mean={nc.mean():.0f} max={nc.max()}")
+    for variant in filter(None, os.environ.get("SOLO_BENCH_SWEEP", "").split(";")):  # diagnostic: option sweep
+        for kv in variant.split(","):
+            key, val = kv.split("=")
+            eng.set_option(key, int(val))
+        ms_v, prof_v, _, _ = timed(step_resident, args.steps, args.warmup, profile=True)
+        log(f"sweep [{variant}] {ms_v / args.steps:.2f} ms/step " +
+            " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof_v.items() if v["ms"] > 0))
+        if os.environ.get("SOLO_BENCH_STATS") == "1":
+            import ctypes as C
+            for z in charges:
+                eng.select_slot(z)
+                eng.search_staged(z, params)
+                eng.synchronize()
+                nq = len(q_by_charge[z]["prec_mz"])
+                cap, cnt = C.c_int32(), np.empty(nq, np.int32)
+                eng._check(eng._lib.solo_debug_scan_dump(eng._h, int(z), nq, C.byref(cap), cnt.ctypes.data_as(C.c_void_p), None))
+                pc = np.percentile(cnt, [1, 50, 90, 99, 100]).astype(int).tolist()
+                log(f"   z={z}: scan-buffer entries/query p1/p50/p90/p99/max = {pc} mean={cnt.mean():.0f}")
     ms_res, prof, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     value = world * nq_rank * args.steps / (ms_res / 1e3)
