@@ -23,7 +23,8 @@ namespace solo {
 
 constexpr int K5_WARPS = 8;
 constexpr int K5_MAXM = 256;   // tentative matches per pair held on chip
-constexpr int K5_MAXSHIFT = 8; // precursor charge <= 7
+constexpr int K5_NBUCKET = 256;   // bucket table entries per library spectrum (fast path)
+constexpr int K5_BUCKET_MZ = 8;    // m/z width of one bucket
 
 struct K5Params {
     const float *q_mz;
@@ -296,6 +297,366 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_best_match_kernel(K5Params p
     }
 }
 
+// ======================================================================= fast path (<= 64 peaks)
+//
+// Same arithmetic and ordering as k5_best_match_kernel, restructured for throughput:
+//  * the next candidate's metadata (one 32-byte record per library spectrum), peaks and bucket
+//    table are fetched into registers while the current candidate is scored (two-deep software
+//    pipeline), candidate ids are fetched 32 at a time;
+//  * the start of the reference's pointer advance comes from a per-spectrum bucket table
+//    (K5_NBUCKET buckets of K5_BUCKET_MZ m/z: number of peaks below the bucket's lower edge, built
+//    once at load time) followed by the reference's own advance loop, instead of a binary search;
+//  * (query peak, shift) combinations are flattened over the lanes, so a 35-peak query with three
+//    shifts takes 4 passes instead of 6.
+
+struct __align__(16) LibMeta {
+    int64_t off;
+    int32_t n;
+    int32_t z;
+    double prec_mz;
+    double pad;
+};
+
+struct K5FastWarpMem {
+    double c_mz[64];
+    unsigned long long keys[K5_MAXM];
+    float c_int[64];
+    uint16_t cur_pairs[64];
+    uint16_t best_pairs[64];
+    uint8_t c_chg[64];
+    __align__(8) uint8_t table[K5_NBUCKET];
+    int count;
+    int pad;
+};
+
+__global__ void k5_build_meta_kernel(const int64_t *__restrict__ off, const double *__restrict__ prec_mz,
+                                     const int32_t *__restrict__ prec_z, int64_t n, LibMeta *__restrict__ meta) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    LibMeta m;
+    m.off = off[r];
+    m.n = (int32_t)(off[r + 1] - off[r]);
+    m.z = prec_z[r];
+    m.prec_mz = prec_mz[r];
+    m.pad = 0.0;
+    meta[r] = m;
+}
+
+// table[r][b] = number of peaks of row r with m/z < b * K5_BUCKET_MZ (saturated at 255)
+__global__ void k5_build_table_kernel(const float *__restrict__ mz, const int64_t *__restrict__ off, int64_t n,
+                                      uint8_t *__restrict__ table) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * K5_NBUCKET) return;
+    const int64_t r = t / K5_NBUCKET;
+    const int b = (int)(t % K5_NBUCKET);
+    const float edge = (float)(b * K5_BUCKET_MZ);
+    const float *m = mz + off[r];
+    int lo = 0, hi = (int)(off[r + 1] - off[r]);
+    while (lo < hi) {  // first peak with mz >= edge
+        const int mid = (lo + hi) >> 1;
+        if (m[mid] < edge) lo = mid + 1;
+        else hi = mid;
+    }
+    table[t] = (uint8_t)min(lo, 255);
+}
+
+void k5_build_aux(solo_handle *h, LibraryStore &L) {
+    L.meta.ensure(std::max<int64_t>(L.n, 1) * sizeof(LibMeta));
+    L.table.ensure(std::max<int64_t>(L.n, 1) * K5_NBUCKET);
+    if (L.n == 0) return;
+    k5_build_meta_kernel<<<div_up(L.n, 256), 256, 0, h->stream>>>(L.off.as<int64_t>(), L.prec_mz.as<double>(),
+                                                                  L.prec_z.as<int32_t>(), L.n, L.meta.as<LibMeta>());
+    k5_build_table_kernel<<<div_up(L.n * K5_NBUCKET, 256), 256, 0, h->stream>>>(L.mz.as<float>(), L.off.as<int64_t>(),
+                                                                                L.n, L.table.as<uint8_t>());
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 2;
+}
+
+struct K5FastParams {
+    K5Params p;
+    const LibMeta *meta;
+    const uint8_t *table;
+};
+
+__global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams fp) {
+    const K5Params &p = fp.p;
+    extern __shared__ __align__(16) unsigned char k5_smem[];
+    K5FastWarpMem *wm_all = reinterpret_cast<K5FastWarpMem *>(k5_smem);
+    __shared__ double s_qmz[64];
+    __shared__ float s_qint[64];
+    __shared__ double s_best_score[K5_WARPS];
+    __shared__ int s_best_pos[K5_WARPS];
+    __shared__ int s_best_np[K5_WARPS];
+    __shared__ int s_best_row[K5_WARPS];
+    constexpr int MAXR = K5_MAXM / 32;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K5FastWarpMem &wm = wm_all[warp];
+    const int q = blockIdx.x;
+    const int64_t qb = p.q_off[q];
+    const int nqp = (int)(p.q_off[q + 1] - qb);
+    const double q_prec = p.q_prec_mz[q];
+    const double tol = p.tol;
+    for (int i = threadIdx.x; i < nqp; i += blockDim.x) {
+        s_qmz[i] = (double)p.q_mz[qb + i];
+        s_qint[i] = p.q_int[qb + i];
+    }
+    __syncthreads();
+
+    const int64_t cb = p.cand_off ? p.cand_off[q] : (int64_t)q * p.cand_stride;
+    const int64_t ce = p.cand_off ? p.cand_off[q + 1] : cb + p.cand_cnt[q];
+    const int64_t ncand = ce - cb;
+    // this warp scores candidates warp, warp + 8, ...: T of them
+    const int64_t T = ncand > warp ? (ncand - warp + K5_WARPS - 1) / K5_WARPS : 0;
+    double best_score = 0.0;
+    int best_pos = -1, best_np = 0, best_rowid = 0x7fffffff;
+
+    // candidate ids, 32 iterations per register; the block after the current one is in flight
+    auto load_ids = [&](int64_t t0) -> int {
+        const int64_t t = t0 + lane;
+        return t < T ? p.cand_ids[cb + warp + t * K5_WARPS] : 0;
+    };
+    int ids_cur = load_ids(0), ids_nxt = load_ids(32);
+
+    // pipeline registers
+    LibMeta m_cur, m_nxt;   // metadata of candidates t and t + 1
+    int row_cur = 0, row_nxt = 0;
+    float pk_mz[2], pk_int[2];
+    uint32_t pk_chg[2];
+    uint2 pk_tab = make_uint2(0u, 0u);
+    static_assert(K5_NBUCKET == 256, "the bucket table is fetched as one uint2 per lane");
+    m_cur.off = 0; m_cur.n = 0; m_cur.z = 0; m_cur.prec_mz = 0.0; m_cur.pad = 0.0;
+    m_nxt = m_cur;
+
+    auto fetch_meta = [&](int row, LibMeta &m) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(&fp.meta[row]);
+        m.off = (int64_t)(((unsigned long long)a.y << 32) | a.x);
+        m.n = (int32_t)a.z;
+        m.z = (int32_t)a.w;
+        m.prec_mz = fp.meta[row].prec_mz;
+    };
+    auto fetch_peaks = [&](int row, const LibMeta &m) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = lane + 32 * r;
+            const bool ok = j < m.n;
+            pk_mz[r] = ok ? p.lib_mz[m.off + j] : 0.f;
+            pk_int[r] = ok ? p.lib_int[m.off + j] : 0.f;
+            pk_chg[r] = ok ? (uint32_t)p.lib_chg[m.off + j] : 0u;
+        }
+        pk_tab = reinterpret_cast<const uint2 *>(fp.table + (size_t)row * K5_NBUCKET)[lane];
+    };
+
+    if (T > 0) {
+        row_cur = __shfl_sync(0xffffffffu, ids_cur, 0);
+        fetch_meta(row_cur, m_cur);
+        fetch_peaks(row_cur, m_cur);
+        if (T > 1) {
+            row_nxt = __shfl_sync(0xffffffffu, ids_cur, 1);
+            fetch_meta(row_nxt, m_nxt);
+        }
+    }
+
+    for (int64_t t = 0; t < T; ++t) {
+        const int row = row_cur;
+        const int n = m_cur.n;
+        const int z = m_cur.z;
+        const double c_prec = m_cur.prec_mz;
+        // ---- registers -> shared memory for candidate t
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = lane + 32 * r;
+            if (j < n) {
+                wm.c_mz[j] = (double)pk_mz[r];
+                wm.c_int[j] = pk_int[r];
+                wm.c_chg[j] = (uint8_t)pk_chg[r];
+            }
+        }
+        reinterpret_cast<uint2 *>(wm.table)[lane] = pk_tab;
+        if (lane == 0) wm.count = 0;
+        __syncwarp();
+        // ---- prefetch: peaks of t + 1 (its metadata arrived during the previous iteration), metadata of t + 2
+        if (t + 1 < T) {
+            m_cur = m_nxt;
+            row_cur = row_nxt;
+            fetch_peaks(row_cur, m_cur);
+            if (t + 2 < T) {
+                const int64_t t2 = t + 2;
+                if ((t2 & 31) == 0) {  // entering a new id block: rotate
+                    ids_cur = ids_nxt;
+                    ids_nxt = load_ids(t2 + 32);
+                }
+                // ids_cur covers the block containing t2 once rotated; before rotation t2 is in the same block as t
+                row_nxt = __shfl_sync(0xffffffffu, ids_cur, (int)(t2 & 31));
+                fetch_meta(row_nxt, m_nxt);
+            }
+        }
+
+        // SpectrumMatch.cpp:18-31
+        const double delta = __dmul_rn(__dsub_rn(q_prec, c_prec), (double)z);
+        const int nshift = (p.allow_shift && fabs(delta) >= tol) ? z + 1 : 1;
+        const double md_lane = (lane > 0 && lane < nshift) ? __ddiv_rn(delta, (double)lane) : 0.0;
+
+        if (n > 0) {
+            const int W = nshift * nqp;
+            const float inv_nqp = 1.0f / (float)nqp;
+            for (int w0 = 0; w0 < W; w0 += 32) {
+                const int w = w0 + lane;
+                const bool active = w < W;
+                // w = s * nqp + i; exact for these small integers
+                const int s = active ? __float2int_rz(((float)w + 0.5f) * inv_nqp) : 0;
+                const int i = active ? w - s * nqp : 0;
+                const double md = __shfl_sync(0xffffffffu, md_lane, s);
+                if (active) {
+                    const double qm = s_qmz[i];
+                    const double thr = __dsub_rn(qm, tol);
+                    // bucket start: every peak below the bucket edge satisfies thr > c_mz + md with a wide margin
+                    // (float rounding at m/z 2000 is 1.2e-4, far inside the 0.004 margin)
+                    int b = __float2int_rd((__double2float_rn(__dsub_rn(thr, md)) - 0.004f) * (1.0f / K5_BUCKET_MZ));
+                    b = max(0, min(K5_NBUCKET - 1, b));
+                    int lo = wm.table[b];
+                    lo = min(lo, n - 1);
+                    while (lo < n - 1 && thr > __dadd_rn(wm.c_mz[lo], md)) ++lo;  // SpectrumMatch.cpp:39-46
+                    for (int j = lo; j < n; ++j) {
+                        const double d = fabs(__dsub_rn(qm, __dadd_rn(wm.c_mz[j], md)));
+                        if (!(d <= tol)) break;
+                        const int cz = wm.c_chg[j];
+                        double mult = 0.0;
+                        if (s == 0) mult = 1.0;
+                        else if (cz == s) mult = 1.0;
+                        else if (cz == 0) mult = 2.0 / 3.0;
+                        if (mult > 0.0) {
+                            const float prod = __double2float_rn(
+                                __dmul_rn(__dmul_rn(mult, (double)s_qint[i]), (double)wm.c_int[j]));
+                            const int slot = atomicAdd(&wm.count, 1);
+                            if (slot < K5_MAXM) {
+                                wm.keys[slot] = ((unsigned long long)float_to_ordered(prod) << 32) |
+                                                ((unsigned long long)(0xFFFFu - (unsigned)i) << 16) |
+                                                (unsigned long long)(0xFFFFu - (unsigned)j);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        int M = wm.count;
+        if (M > K5_MAXM) {  // reported, never silently truncated
+            if (lane == 0) atomicAdd(p.overflow, 1);
+            M = K5_MAXM;
+        }
+
+        // rank sort, descending, in place
+        if (M > 1) {
+            unsigned long long mine[MAXR];
+            int rank[MAXR];
+            const int R = (M + 31) >> 5;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const int idx = lane + 32 * r;
+                mine[r] = (r < R && idx < M) ? wm.keys[idx] : 0ull;
+                rank[r] = 0;
+            }
+            for (int j = 0; j < M; ++j) {
+                const unsigned long long kj = wm.keys[j];
+#pragma unroll
+                for (int r = 0; r < MAXR; ++r) {
+                    if (r < R) {
+                        const int idx = lane + 32 * r;
+                        rank[r] += (kj > mine[r]) || (kj == mine[r] && j < idx);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const int idx = lane + 32 * r;
+                if (r < R && idx < M) wm.keys[rank[r]] = mine[r];
+            }
+            __syncwarp();
+        }
+
+        // greedy assignment (SpectrumMatch.cpp:95-111), warp-uniform
+        double score = 0.0;
+        int np = 0;
+        unsigned long long qu = 0ull, cu = 0ull;
+        const int max_np = min(nqp, n);
+        for (int m = 0; m < M && np < max_np; ++m) {
+            const unsigned long long key = wm.keys[m];
+            const int i = 0xFFFF - (int)((key >> 16) & 0xFFFFu);
+            const int j = 0xFFFF - (int)(key & 0xFFFFu);
+            if (!(((qu >> i) | (cu >> j)) & 1ull)) {
+                score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(key >> 32)));
+                if (lane == 0) wm.cur_pairs[np] = (uint16_t)((i << 8) | j);
+                ++np;
+                qu |= 1ull << i;
+                cu |= 1ull << j;
+            }
+        }
+
+        // SpectrumMatch.cpp:118 — first candidate, then strictly greater only
+        const int pos = (int)(warp + t * K5_WARPS);
+        if (best_pos < 0 || best_score < score || (p.tie_by_row && best_score == score && row < best_rowid)) {
+            best_score = score;
+            best_pos = pos;
+            best_rowid = row;
+            best_np = np;
+            __syncwarp();
+            for (int u = lane; u < np; u += 32) wm.best_pairs[u] = wm.cur_pairs[u];
+        }
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        s_best_score[warp] = best_score;
+        s_best_pos[warp] = best_pos;
+        s_best_np[warp] = best_np;
+        s_best_row[warp] = best_rowid;
+    }
+    __syncthreads();
+    // winner: maximum score, ties -> earliest candidate position (== the sequential rule)
+    int win = -1;
+    double ws = 0.0;
+    int wp = -1, wr = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < K5_WARPS; ++w) {
+        const int pos = s_best_pos[w];
+        const double sc = s_best_score[w];
+        const int rw = s_best_row[w];
+        const bool earlier = p.tie_by_row ? (rw < wr) : (pos < wp);
+        if (pos >= 0 && (win < 0 || sc > ws || (sc == ws && earlier))) {
+            win = w;
+            ws = sc;
+            wp = pos;
+            wr = rw;
+        }
+    }
+    if (win < 0) {
+        if (threadIdx.x == 0) {
+            p.best_pos[q] = -1;
+            if (p.best_row) p.best_row[q] = -1;
+            p.best_score[q] = 0.0;
+            p.n_pairs[q] = 0;
+        }
+        return;
+    }
+    if (warp == win) {
+        const int np = s_best_np[win];
+        if (lane == 0) {
+            p.best_pos[q] = wp;
+            if (p.best_row) p.best_row[q] = wr;
+            p.best_score[q] = ws;
+            p.n_pairs[q] = np;
+        }
+        uint32_t *out = p.pairs + (size_t)q * p.max_pairs * 2;
+        for (int u = lane; u < np && u < p.max_pairs; u += 32) {
+            const uint16_t pr = wm.best_pairs[u];
+            out[2 * u] = pr >> 8;
+            out[2 * u + 1] = pr & 0xFFu;
+        }
+    }
+}
+
 template <int PPL>
 static void launch_k5(solo_handle *h, const K5Params &p, int nq) {
     auto k = k5_best_match_kernel<PPL>;
@@ -337,7 +698,17 @@ void launch_best_match(solo_handle *h, const ScoreArgs &a) {
     p.pairs = a.pairs;
     p.overflow = a.overflow;
     StageTimer t(h, ST_SCORE, 1);
-    if (maxp <= 64) launch_k5<2>(h, p, a.nq);
+    static const bool v_old = getenv("SOLO_K5_OLD") != nullptr;
+    if (maxp <= 64 && L.meta.p && !v_old) {
+        K5FastParams fp;
+        fp.p = p;
+        fp.meta = L.meta.as<LibMeta>();
+        fp.table = L.table.as<uint8_t>();
+        const size_t smem = sizeof(K5FastWarpMem) * K5_WARPS;
+        SOLO_CUDA(cudaFuncSetAttribute(k5_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k5_fast_kernel<<<a.nq, K5_WARPS * 32, smem, h->stream>>>(fp);
+        SOLO_CUDA(cudaGetLastError());
+    } else if (maxp <= 64) launch_k5<2>(h, p, a.nq);
     else launch_k5<4>(h, p, a.nq);
 }
 

@@ -205,7 +205,7 @@ void solo_destroy(solo_handle *h) {
     rel(h->lut);
     for (auto &kv : h->libs) {
         LibraryStore &L = kv.second;
-        rel(L.mz); rel(L.inten); rel(L.chg); rel(L.off); rel(L.prec_mz); rel(L.prec_mz32); rel(L.prec_z); rel(L.valid);
+        rel(L.mz); rel(L.inten); rel(L.chg); rel(L.off); rel(L.prec_mz); rel(L.prec_mz32); rel(L.prec_z); rel(L.valid); rel(L.meta); rel(L.table);
     }
     for (auto &kv : h->ivf) {
         IvfIndex &x = kv.second;
@@ -360,6 +360,7 @@ int solo_load_library(solo_handle *h, int charge, const float *mz, const float *
             L.valid.ensure(std::max<int64_t>(n, 16));
             SOLO_CUDA(cudaMemsetAsync(L.valid.p, 1, std::max<int64_t>(n, 16), h->stream));
         }
+        k5_build_aux(h, L);
         SOLO_CUDA(cudaStreamSynchronize(h->stream));
     });
 }

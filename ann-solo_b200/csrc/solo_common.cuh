@@ -122,6 +122,7 @@ struct LibraryStore {
     int64_t n_peaks = 0;
     int max_peaks = 0;
     DevBuf mz, inten, chg, off, prec_mz, prec_mz32, prec_z, valid;
+    DevBuf meta, table;  // scorer fast path: packed per-row metadata and m/z bucket tables (k5_build_aux)
 };
 
 // ---------------------------------------------------------------- IVF index
@@ -269,5 +270,6 @@ struct ScoreArgs {
     int32_t *overflow;   // device counter of match-list overflows
 };
 void launch_best_match(solo_handle *h, const ScoreArgs &a);
+void k5_build_aux(solo_handle *h, LibraryStore &L);
 
 }  // namespace solo
