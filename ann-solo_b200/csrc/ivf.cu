@@ -686,8 +686,8 @@ constexpr int TK_THREADS = 1024;
 // round-0 part [0, n0) that still passes, mark non-overflowed queries done (tau = +inf).
 __global__ void __launch_bounds__(TK_THREADS)
 threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt, int32_t *__restrict__ n0,
-                 float *__restrict__ tau, int cap, int k, EpsArgs ea, int retry) {
-    extern __shared__ uint32_t s_keys[];  // [cap]
+                 float *__restrict__ tau, int cap, int scap, int k, EpsArgs ea, int retry) {
+    extern __shared__ uint32_t s_keys[];  // [scap] (scap <= 32 * blockDim.x)
     __shared__ uint32_t s_hist[KTH_BINS];
     __shared__ uint32_t s_bc[KTH_BC];
     __shared__ int s_out;
@@ -701,7 +701,7 @@ threshold_kernel(unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt
         }
     }
     const int n = min(raw, cap);
-    if (n < k) {
+    if (n < k || n > scap) {  // too few to bound the k-th score — or more than this launch holds: no threshold (still exact)
         if (threadIdx.x == 0) {
             tau[q] = -INFINITY;
             n0[q] = n;
@@ -742,7 +742,9 @@ struct FinalArgs {
     const int32_t *list_ids;
     int cap;
     int k;
-    int32_t *overflow;     // incremented when cnt > cap
+    int scap;              // entries this launch holds in shared memory; queries with more are deferred
+    int min_cnt;           // process only queries with more than min_cnt entries (second pass)
+    int32_t *overflow;     // [0] incremented when cnt > cap, [1] when deferred (cnt > scap)
     // sorted API output
     int64_t *I;
     float *D;
@@ -792,18 +794,27 @@ __device__ __forceinline__ bool window_pass(const FinalArgs &a, int q, int id) {
 //     it returns exact scores D).
 //  3. the remaining slots are filled with the best band entries under (exact score desc, id asc).
 // With an exact scan engine (eps.rel == 0) step 2 is the identity.
+constexpr int TK_BCAP = 1024;  // band entries re-scored on chip by the fast path of final_topk_kernel
+
 __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
-    extern __shared__ uint32_t s_keys[];  // [cap] decision keys; s_q follows
+    extern __shared__ uint32_t s_keys[];  // [scap] decision keys; s_q [d] follows; then s_sorted [IVF_MAX_K] (sorted output)
     __shared__ uint32_t s_hist[KTH_BINS];
     __shared__ uint32_t s_bc[KTH_BC];
-    __shared__ int s_nout, s_neq;
-    __shared__ unsigned long long s_sorted[IVF_MAX_K];
-    float *s_q = reinterpret_cast<float *>(s_keys + a.cap);
+    __shared__ int s_nout, s_neq, s_nband, s_ncert;
+    __shared__ uint32_t s_band_pos[TK_BCAP];
+    __shared__ unsigned long long s_band_key[TK_BCAP];
+    float *s_q = reinterpret_cast<float *>(s_keys + a.scap);
+    unsigned long long *s_sorted = reinterpret_cast<unsigned long long *>(s_q + ((a.d + 1) & ~1));
     const int q = blockIdx.x;
     const unsigned long long *b = a.buf + (int64_t)q * a.cap;
     const int raw = a.cnt[q];
+    if (raw <= a.min_cnt) return;  // finished by the first pass
     if (raw > a.cap) {
         if (threadIdx.x == 0) atomicAdd(a.overflow, 1);
+        return;
+    }
+    if (raw > a.scap) {
+        if (threadIdx.x == 0) atomicAdd(a.overflow + 1, 1);
         return;
     }
     const int n = raw;
@@ -812,9 +823,70 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     if (threadIdx.x == 0) {
         s_nout = 0;
         s_neq = 0;
+        s_nband = 0;
+        s_ncert = 0;
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(b[i] >> 32)));
     __syncthreads();
+    if (kk > 0 && a.eps.rel > 0.f && !sorted_out) {
+        // ---- fast path: everything above the band is in; the (small) band is re-scored exactly, one
+        // warp per entry, and ranked under (exact score desc, id asc)
+        int gt;
+        const uint32_t T = block_kth_largest_u32(s_keys, n, kk, false, 0u, s_hist, s_bc, &gt);
+        const float t = ivf_o2f(T);
+        const float e2 = 2.f * band_eps(a.eps, t, q);
+        const float lo = t - e2, hi = t + e2;
+        for (int j = threadIdx.x; j < a.d; j += blockDim.x) s_q[j] = a.q[(int64_t)q * a.d + j];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float s = ivf_o2f(s_keys[i]);
+            if (s > hi) {
+                atomicAdd(&s_ncert, 1);
+                const int id = a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)];
+                if (window_pass(a, q, id)) a.sel_ids[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] = id;
+            } else if (s >= lo) {
+                const int p = atomicAdd(&s_nband, 1);
+                if (p < TK_BCAP) s_band_pos[p] = (uint32_t)(b[i] & 0xFFFFFFFFull);
+            }
+        }
+        __syncthreads();
+        const int nband = s_nband;
+        if (nband <= TK_BCAP) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+            for (int w = warp; w < nband; w += nwarps) {
+                const uint32_t pos = s_band_pos[w];
+                const int64_t rb = a.sp_off[pos], re = a.sp_off[pos + 1];
+                float acc = 0.f;
+                for (int64_t e0 = rb; e0 < re; e0 += 32) {
+                    const int64_t e = e0 + lane;
+                    const float qv = e < re ? s_q[a.sp_idx[e]] : 0.f;
+                    const float xv = e < re ? a.sp_val[e] : 0.f;
+                    const int cnt = (int)min((int64_t)32, re - e0);
+                    for (int u = 0; u < cnt; ++u)
+                        acc = __fmaf_rn(__shfl_sync(0xffffffffu, qv, u), __shfl_sync(0xffffffffu, xv, u), acc);
+                }
+                if (lane == 0)
+                    s_band_key[w] = ((unsigned long long)((acc == acc) ? ivf_f2o(acc) : 0u) << 32) |
+                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)a.list_ids[pos]);
+            }
+            __syncthreads();
+            const int need = kk - s_ncert;
+            for (int w = threadIdx.x; w < nband; w += blockDim.x) {
+                const unsigned long long key = s_band_key[w];
+                int r = 0;
+                for (int w2 = 0; w2 < nband; ++w2) r += s_band_key[w2] > key;
+                if (r < need) {
+                    const int id = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+                    if (window_pass(a, q, id)) a.sel_ids[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] = id;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) a.sel_cnt[q] = s_nout;
+            return;
+        }
+        __syncthreads();  // band larger than the on-chip list: generic path below (s_keys still hold approximate keys)
+        if (threadIdx.x == 0) s_nout = 0;
+        __syncthreads();
+    }
     if (kk > 0) {
         int gt;
         if (a.eps.rel > 0.f) {
@@ -1332,7 +1404,16 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     const size_t en_smem = (size_t)EN_ENT * sizeof(uint2) + (EN_VCH + 4) * sizeof(int) + (size_t)EN_WARPS * d * sizeof(float);
     SOLO_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)en_smem));
     const int ysplit = std::max(1, std::min(64, div_up(kNumSMs * 8, nlist)));
-    const size_t tk_smem = (size_t)cap * sizeof(uint32_t) + (size_t)d * sizeof(float);
+    // K4 shared memory: keys + the query (+ the sorted output rows); the common case runs with a small
+    // key capacity and several CTAs per SM, the rare large query is deferred to a second, big launch
+    const bool sorted_out = a.I != nullptr;
+    auto tk_bytes = [&](int keys) {
+        return (size_t)keys * sizeof(uint32_t) + (size_t)((d + 1) & ~1) * sizeof(float) +
+               (sorted_out ? (size_t)IVF_MAX_K * sizeof(unsigned long long) : 0);
+    };
+    const int scap_thr = (int)std::min<int64_t>(cap, std::max<int64_t>(c0, a.k));   // round 0 appends <= c0 per query
+    const int scap_fin = std::min(cap, 8192);
+    const size_t tk_smem = tk_bytes(cap);
     SOLO_CUDA(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     // expected scanned vectors per query, for the flop figure of the stage
@@ -1352,8 +1433,8 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     run_round(0);
     {
         StageTimer t(h, ST_TOPK, 1);
-        threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
-                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, ea, 0);
+        threshold_kernel<<<nq, scap_thr <= 16384 ? 512 : TK_THREADS, tk_bytes(scap_thr), st>>>(
+            buf.as<unsigned long long>(), cnt.as<int32_t>(), n0.as<int32_t>(), tau.as<float>(), cap, scap_thr, a.k, ea, 0);
         SOLO_CUDA(cudaGetLastError());
     }
     FinalArgs fa;
@@ -1388,20 +1469,34 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         run_round(1);
         {
             StageTimer t(h, ST_TOPK, 1);
-            final_topk_kernel<<<nq, TK_THREADS, tk_smem, st>>>(fa);
+            fa.scap = scap_fin;
+            fa.min_cnt = -1;
+            final_topk_kernel<<<nq, 512, tk_bytes(scap_fin), st>>>(fa);
             SOLO_CUDA(cudaGetLastError());
         }
         // A query whose candidate buffer overflowed was not finished: raise its threshold from
-        // what the buffer holds and rescan (never truncate). One 4-byte read-back per batch.
-        int32_t n_over = 0;
-        SOLO_CUDA(cudaMemcpyAsync(&n_over, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        // what the buffer holds and rescan (never truncate). One 8-byte read-back per batch:
+        // [0] overflowed queries, [1] queries deferred to the large-capacity launch.
+        int32_t n_flags[2] = {0, 0};
+        SOLO_CUDA(cudaMemcpyAsync(n_flags, ovf.p, sizeof n_flags, cudaMemcpyDeviceToHost, st));
         SOLO_CUDA(cudaStreamSynchronize(st));
+        if (n_flags[1] > 0) {
+            SOLO_CUDA(cudaMemsetAsync(ovf.as<int32_t>() + 1, 0, sizeof(int32_t), st));
+            StageTimer t(h, ST_TOPK, 1);
+            fa.scap = cap;
+            fa.min_cnt = scap_fin;
+            final_topk_kernel<<<nq, TK_THREADS, tk_smem, st>>>(fa);
+            SOLO_CUDA(cudaGetLastError());
+            SOLO_CUDA(cudaMemcpyAsync(n_flags, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            SOLO_CUDA(cudaStreamSynchronize(st));
+        }
+        const int32_t n_over = n_flags[0];
         if (n_over == 0) break;
         SOLO_REQUIRE(attempt < 8, SOLO_ECAPACITY, "candidate buffer overflow persists for %d queries", n_over);
         SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int32_t), st));
         StageTimer t(h, ST_TOPK, 1);
         threshold_kernel<<<nq, TK_THREADS, tk_smem, st>>>(buf.as<unsigned long long>(), cnt.as<int32_t>(),
-                                                          n0.as<int32_t>(), tau.as<float>(), cap, a.k, ea, 1);
+                                                          n0.as<int32_t>(), tau.as<float>(), cap, cap, a.k, ea, 1);
         SOLO_CUDA(cudaGetLastError());
     }
 }
