@@ -1156,6 +1156,10 @@ void ivf_finalize(solo_handle *h, IvfIndex &ix) {
     }
     // stable bucket by list: insertion order inside every list, as Faiss `add` leaves them
     ix.h_list_off.assign(nlist + 1, 0);
+    const bool sharded = (int)ix.owned.size() == nlist;
+    if (sharded)  // rows of lists another GPU owns are not stored (their ids stay reserved)
+        for (int64_t i = 0; i < n; ++i)
+            if (row_list[i] >= 0 && !ix.owned[row_list[i]]) row_list[i] = -1;
     for (int64_t i = 0; i < n; ++i)
         if (row_list[i] >= 0) ix.h_list_off[row_list[i] + 1]++;
     ix.max_list_len = 0;

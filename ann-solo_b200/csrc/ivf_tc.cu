@@ -22,7 +22,7 @@ namespace solo {
 
 constexpr int TC_BM = 128;       // queries per accumulator tile (MMA M)
 constexpr int TC_BK = 64;        // fp16 elements per k-block = 128 bytes = one swizzle atom row
-constexpr int TC_STAGES = 4;     // A (query) stages
+constexpr int TC_MAX_STAGES = 12; // A (query) stages: as many as fit next to the resident list chunk
 constexpr int TC_BOX = 32;       // rows per TMA box
 constexpr int TC_A_BYTES = TC_BM * 128;
 constexpr int TC_MAX_KB = 24;    // dim <= 1536
@@ -165,6 +165,7 @@ struct TcScanArgs {
     int nlist;
     int dim;
     int nb;                   // chunk capacity NB (multiple of 32)
+    int stages;               // A stages in the ring
     float inv_scale;          // 2^-(scale_index + scale_query)
     const float *tau;         // [nq]
     unsigned long long *buf;  // [nq][cap]
@@ -188,8 +189,8 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 }
 
 struct __align__(8) TcBarriers {
-    unsigned long long full_a[TC_STAGES];
-    unsigned long long empty_a[TC_STAGES];
+    unsigned long long full_a[TC_MAX_STAGES];
+    unsigned long long empty_a[TC_MAX_STAGES];
     unsigned long long full_b[TC_MAX_KB];
     unsigned long long empty_b[TC_MAX_KB];
     unsigned long long tmem_full[2];
@@ -250,7 +251,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     const int num_kb = NUM_KB > 0 ? NUM_KB : (a.dim + TC_BK - 1) / TC_BK;
     const int b_kb_bytes = a.nb * 128;
     unsigned char *sA = tc_smem;
-    unsigned char *sB = tc_smem + TC_STAGES * TC_A_BYTES;
+    const int n_stages = a.stages;
+    unsigned char *sB = tc_smem + n_stages * TC_A_BYTES;
     TcBarriers *bars = reinterpret_cast<TcBarriers *>(sB + (size_t)num_kb * b_kb_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,7 +261,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     unsigned long long pw0 = 0, pw1 = 0, pw2 = 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < TC_MAX_STAGES; ++s) {
             mbar_init(smem_u32(&bars->full_a[s]), TC_PRODUCERS);  // the A-producer threads
             mbar_init(smem_u32(&bars->empty_a[s]), 1);            // tcgen05.commit
         }
@@ -424,7 +426,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         // Uniform control flow for the whole warp; one elected lane issues tcgen05.mma / commit.
         const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-        static_assert((TC_STAGES & (TC_STAGES - 1)) == 0, "TC_STAGES must be a power of two");
         uint32_t stage = 0, phase = 0, unit = 0, n_local = 0;
         bool ready = false;  // outcome of the early probe of full_a[stage]
         const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
@@ -441,7 +442,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                 if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb]), n_local & 1, prof_on, pw1);
                 if (!ready) mbar_wait_prof(smem_u32(&bars->full_a[stage]), phase, prof_on, pw2);
                 // probe the next stage's barrier now; the answer is needed one k-block later
-                const uint32_t nstage = (stage + 1) & (TC_STAGES - 1);
+                const uint32_t nstage = stage + 1 == (uint32_t)n_stages ? 0u : stage + 1;
                 const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
                 const bool ready_next = mbar_try_wait(smem_u32(&bars->full_a[nstage]), nphase);
                 tc_fence_after();
@@ -547,7 +548,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                         cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
                 }
                 cp_async_arrive_noinc(smem_u32(&bars->full_a[stage]));
-                if (++stage == TC_STAGES) {
+                if (++stage == (uint32_t)n_stages) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -723,12 +724,20 @@ static void tc_prof_report(solo_handle *h, const char *what, int ctas) {
     fprintf(stderr, " (mean/max kcycles per CTA)\n");
 }
 
-// chunk capacity NB: the largest multiple of 32 (<= 256) whose resident B region fits next to the A stages
-static int tc_chunk_rows(const IvfIndex &ix) {
+// Shared-memory split: the resident list chunk (NB rows x num_kb k-blocks) and the ring of query
+// stages. The ring is what hides the L2 latency of the query gather, so NB is kept as small as the
+// list lengths allow: the largest multiple of 32 that still leaves at least four stages, but not
+// larger than needed for the longest list (SOLO_TC_NB overrides, for experiments).
+static void tc_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out, int nb_cap = 256) {
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
-    const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64 - TC_STAGES * TC_A_BYTES;
-    int nb = avail / (num_kb * 128) / 32 * 32;
-    return std::min(nb, 256);
+    const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64;
+    int nb = (avail - 4 * TC_A_BYTES) / (num_kb * 128) / 32 * 32;
+    nb = std::min(nb, nb_cap / 32 * 32);
+    static const int env_nb = getenv("SOLO_TC_NB") ? atoi(getenv("SOLO_TC_NB")) : 0;
+    if (env_nb >= 32 && env_nb <= nb) nb = env_nb / 32 * 32;
+    int stages = nb >= 32 ? (avail - num_kb * nb * 128) / TC_A_BYTES : 0;
+    *nb_out = nb;
+    *stages_out = std::min(stages, TC_MAX_STAGES);
 }
 
 void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int nq, int q_scale_log2, __half *qh,
@@ -744,8 +753,9 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
                     int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
     SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
     const int nlist = ix.nlist;
-    const int nb = tc_chunk_rows(ix);
-    SOLO_REQUIRE(nb >= 32, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
+    int nb, stages;
+    tc_smem_plan(ix, &nb, &stages);
+    SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     item_cnt.ensure((size_t)nlist * sizeof(int32_t));
     item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
     // every list contributes at most ceil(len / nb) <= len / nb + 1 items
@@ -764,6 +774,7 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     a.nlist = nlist;
     a.dim = ix.dim;
     a.nb = nb;
+    a.stages = stages;
     a.inv_scale = ldexpf(1.f, -(ix.scale_log2 + q_scale_log2));
     a.tau = tau;
     a.buf = buf;
@@ -775,7 +786,7 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     static const int v_debug = getenv("SOLO_TC_DEBUG") ? atoi(getenv("SOLO_TC_DEBUG")) : 0;
     a.debug = v_debug;
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
-    const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
+    const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
     SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
     CUtensorMap map;
     memcpy(&map, ix.tmap_storage, sizeof map);
@@ -796,8 +807,9 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
 void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int nq, int q_scale_log2,
                       float *out, int ld) {
     SOLO_REQUIRE(ix.tmap_cent_valid, SOLO_ESTATE, "centroid tensor map missing");
-    const int nb = tc_chunk_rows(ix);
-    SOLO_REQUIRE(nb >= 32, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
+    int nb, stages;
+    tc_smem_plan(ix, &nb, &stages, 64);  // every centroid chunk sees every query: short chunks, deep query ring
+    SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     const int n_items = div_up(ix.nlist, nb);
     if (ix.coarse_items_nq != nq) {  // descriptors are tiny: built on the host, [count pair | items], cached per nq
         std::vector<unsigned char> hbuf(sizeof(int64_t) * 2 + (size_t)n_items * sizeof(TcItem));
@@ -827,12 +839,13 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     a.nlist = 1;
     a.dim = ix.dim;
     a.nb = nb;
+    a.stages = stages;
     a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
     a.dense_out = out;
     a.dense_ld = ld;
     a.prof = tc_prof_buffer();
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
-    const size_t smem = (size_t)TC_STAGES * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
+    const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
     CUtensorMap map;
     memcpy(&map, ix.tmap_cent_storage, sizeof map);
     auto kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 3> : scan_tc_kernel<1, 0, 1, 3>;

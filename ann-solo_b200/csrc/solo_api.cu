@@ -799,6 +799,182 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
     return solo_fetch_results(h, best_row, best_score, n_pairs, pairs, n_cand);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------- mode B: inverted lists sharded over GPUs
+
+namespace solo {
+
+// merge `parts` sorted (score desc, id asc) top-k rows per query into one: rank of an element = its
+// position in its own part + number of greater keys in every other part (binary search); ids are
+// unique across parts (every library row is stored on exactly one GPU), -1 ids are padding.
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const float *__restrict__ D, const int64_t *__restrict__ I, int parts, int nq, int k, int q_begin,
+                  float *__restrict__ Do, int64_t *__restrict__ Io) {
+    const int ql = blockIdx.x, q = q_begin + ql;
+    auto key_of = [&](int p, int i) -> unsigned long long {
+        const int64_t id = I[((int64_t)p * nq + q) * k + i];
+        if (id < 0) return 0ull;
+        return ((unsigned long long)ivf_f2o(D[((int64_t)p * nq + q) * k + i]) << 32) |
+               (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+    };
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        Io[(int64_t)ql * k + i] = -1;
+        Do[(int64_t)ql * k + i] = -INFINITY;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < parts * k; e += blockDim.x) {
+        const int p = e / k, i = e % k;
+        const unsigned long long key = key_of(p, i);
+        if (key == 0ull) continue;
+        int rank = i;
+        for (int p2 = 0; p2 < parts && rank < k; ++p2) {
+            if (p2 == p) continue;
+            int lo = 0, hi = k;  // number of keys in part p2 greater than key (parts are sorted descending)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (key_of(p2, mid) > key) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            Io[(int64_t)ql * k + rank] = I[((int64_t)p * nq + q) * k + i];
+            Do[(int64_t)ql * k + rank] = D[((int64_t)p * nq + q) * k + i];
+        }
+    }
+}
+
+// candidate lists from given top-k ids: precursor window AND valid (spectral_library.py:441-454)
+__global__ void __launch_bounds__(256)
+filter_ids_kernel(const int64_t *__restrict__ I, int k, const double *__restrict__ q_prec_mz,
+                  const float *__restrict__ lib_prec_mz32, const uint8_t *__restrict__ lib_valid, int64_t n_lib, int charge,
+                  double tol, int mode, int32_t *__restrict__ sel_ids, int32_t *__restrict__ sel_cnt) {
+    __shared__ int s_n;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const double qm = q_prec_mz[q];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const int64_t id = I[(int64_t)q * k + i];
+        if (id >= 0 && id < n_lib && lib_valid[id] && window_ok(qm, lib_prec_mz32[id], charge, tol, mode))
+            sel_ids[(int64_t)q * k + atomicAdd(&s_n, 1)] = (int32_t)id;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sel_cnt[q] = s_n;
+}
+
+}  // namespace solo
+
+extern "C" {
+
+int solo_ivf_set_owned_lists(solo_handle *h, int charge, const uint8_t *owned, int nlist) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        if (!owned) {
+            ix.owned.clear();
+        } else {
+            SOLO_REQUIRE(nlist == ix.nlist, SOLO_EINVAL, "owned mask has %d entries, the index has %d lists", nlist, ix.nlist);
+            ix.owned.assign(owned, owned + nlist);
+        }
+        ix.dirty = true;
+    });
+}
+
+int solo_ivf_search_staged(solo_handle *h, int charge, int k, int nprobe, int64_t *d_I, float *d_D) {
+    if (!h || !d_I) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
+        const int nq = h->nq;
+        if (nq == 0) return;
+        DevBuf &qv = h->scratch[19];
+        qv.ensure((size_t)nq * h->hash_len * sizeof(float));
+        const void *mzv = h->q_mz_is_f64 < 0 ? h->q_mz.p : h->q_mz_vec.p;
+        launch_vectorize(h, mzv, h->q_mz_is_f64 > 0 ? 1 : 0, h->q_int.as<float>(), h->q_off.as<int64_t>(), nq, h->q_peaks,
+                         1, qv.as<float>(), nullptr, 0);
+        IvfSearchArgs s;
+        memset(&s, 0, sizeof s);
+        s.q = qv.as<float>();
+        s.nq = nq;
+        s.k = k;
+        s.nprobe = nprobe;
+        s.I = d_I;
+        s.D = d_D;
+        s.win_tol_mode = -1;
+        ivf_search(h, ix, s);
+    });
+}
+
+int solo_merge_topk_device(solo_handle *h, const float *d_D_parts, const int64_t *d_I_parts, int parts, int nq, int k,
+                           int q_begin, int nq_out, float *d_D, int64_t *d_I) {
+    if (!h || !d_D_parts || !d_I_parts || !d_D || !d_I) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(parts >= 1 && k >= 1 && q_begin >= 0 && nq_out >= 0 && q_begin + nq_out <= nq, SOLO_EINVAL,
+                     "bad merge shape");
+        if (nq_out == 0) return;
+        StageTimer t(h, ST_TOPK, 1);
+        merge_topk_kernel<<<nq_out, 256, 0, h->stream>>>(d_D_parts, d_I_parts, parts, nq, k, q_begin, d_D, d_I);
+        SOLO_CUDA(cudaGetLastError());
+    });
+}
+
+int solo_score_staged_ids(solo_handle *h, int charge, const solo_search_params *p, const int64_t *d_I, int q_begin,
+                          int nq_slice) {
+    if (!h || !p || !d_I) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        LibraryStore &L = get_lib(h, charge);
+        const int nq = h->nq;
+        SOLO_REQUIRE(p->tol_mode == SOLO_TOL_DA || p->tol_mode == SOLO_TOL_PPM, SOLO_EINVAL,
+                     "Unknown precursor tolerance mode");
+        SOLO_REQUIRE(p->max_pairs > 0 && p->k >= 1, SOLO_EINVAL, "bad parameters");
+        SOLO_REQUIRE(q_begin >= 0 && nq_slice >= 0 && q_begin + nq_slice <= nq, SOLO_EINVAL, "query slice out of range");
+        if (h->r_nq != nq || h->r_max_pairs != p->max_pairs) ensure_results(h, nq, p->max_pairs);
+        if (nq_slice == 0) return;
+        DevBuf &ovf = h->r_ovf, &sel = h->scratch[20], &dpos = h->scratch[23];
+        ovf.ensure(16);
+        SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
+        sel.ensure((size_t)nq_slice * p->k * sizeof(int32_t));
+        dpos.ensure((size_t)nq * sizeof(int32_t));
+        {
+            StageTimer t(h, ST_CANDIDATES, 1);
+            filter_ids_kernel<<<nq_slice, 256, 0, h->stream>>>(d_I, p->k, h->q_prec_mz.as<double>() + q_begin,
+                                                               L.prec_mz32.as<float>(), L.valid.as<uint8_t>(), L.n, charge,
+                                                               p->tol_value, p->tol_mode, sel.as<int32_t>(),
+                                                               h->r_n_cand.as<int32_t>() + q_begin);
+            SOLO_CUDA(cudaGetLastError());
+        }
+        ScoreArgs a;
+        a.q_mz = h->q_mz.as<float>();
+        a.q_int = h->q_int.as<float>();
+        a.q_off = h->q_off.as<int64_t>() + q_begin;  // CSR offsets are absolute: a shifted view is a valid batch
+        a.q_prec_mz = h->q_prec_mz.as<double>() + q_begin;
+        a.nq = nq_slice;
+        a.q_max_peaks = h->q_max_peaks;
+        a.lib = &L;
+        a.tol = p->fragment_mz_tolerance;
+        a.allow_shift = p->allow_shift;
+        a.max_pairs = p->max_pairs;
+        a.best_pos = dpos.as<int32_t>() + q_begin;
+        a.best_row = h->r_best_row.as<int32_t>() + q_begin;
+        a.best_score = h->r_best_score.as<double>() + q_begin;
+        a.n_pairs = h->r_n_pairs.as<int32_t>() + q_begin;
+        a.pairs = h->r_pairs.as<uint32_t>() + (size_t)q_begin * p->max_pairs * 2;
+        a.overflow = ovf.as<int32_t>();
+        a.tie_by_row = 1;
+        a.cand_ids = sel.as<int32_t>();
+        a.cand_off = nullptr;
+        a.cand_cnt = h->r_n_cand.as<int32_t>() + q_begin;
+        a.cand_stride = p->k;
+        launch_best_match(h, a);
+    });
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ---------------------------------------------------------------- instrumentation
 
 int solo_profile_enable(solo_handle *h, int on) {

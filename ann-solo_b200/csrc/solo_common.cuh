@@ -148,6 +148,7 @@ struct IvfIndex {
     DevBuf sp_val;          // float  [nnz]
     DevBuf row_list;        // int32 [ntotal] list of row (-1 = skipped)
     std::vector<int64_t> h_list_off;  // host copy
+    std::vector<uint8_t> owned;       // mode B (lists sharded over GPUs): owned[l] == 0 -> list l is not stored here; empty = all
     // every row ever added, in insertion order, as sparse rows (lists are rebuilt from these)
     DevBuf row_off;         // int64 [ntotal+1]
     DevBuf row_idx;         // uint16 [nnz]

@@ -254,6 +254,32 @@ class SoloEngine:
         self.search_staged(charge, params)
         return self.fetch_results(out)
 
+    # ------------------------------------------------------------------ mode B (lists sharded over GPUs)
+    def ivf_set_owned_lists(self, charge: int, owned: Optional[np.ndarray]):
+        """owned[l] != 0: list l is stored on this GPU (None: all lists)."""
+        if owned is None:
+            self._check(self._lib.solo_ivf_set_owned_lists(self._h, int(charge), None, 0))
+        else:
+            o = _c(owned, np.uint8)
+            self._check(self._lib.solo_ivf_set_owned_lists(self._h, int(charge), _ptr(o), len(o)))
+
+    def ivf_search_staged(self, charge: int, k: int, nprobe: int, d_I: int, d_D: int):
+        """Search this GPU's lists for the staged batch; d_I / d_D are device pointers of (nq, k)
+        int64 / float32 buffers (e.g. torch tensors' data_ptr())."""
+        self._check(self._lib.solo_ivf_search_staged(self._h, int(charge), int(k), int(nprobe), C.c_void_p(d_I),
+                                                     C.c_void_p(d_D)))
+
+    def merge_topk_device(self, d_D_parts: int, d_I_parts: int, parts: int, nq: int, k: int, q_begin: int, nq_out: int,
+                          d_D: int, d_I: int):
+        self._check(self._lib.solo_merge_topk_device(self._h, C.c_void_p(d_D_parts), C.c_void_p(d_I_parts), int(parts),
+                                                     int(nq), int(k), int(q_begin), int(nq_out), C.c_void_p(d_D),
+                                                     C.c_void_p(d_I)))
+
+    def score_staged_ids(self, charge: int, params: SearchParams, d_I: int, q_begin: int, nq_slice: int):
+        self._check(self._lib.solo_score_staged_ids(self._h, int(charge), C.byref(params), C.c_void_p(d_I), int(q_begin),
+                                                    int(nq_slice)))
+        self._staged_max_pairs = params.max_pairs
+
     # ------------------------------------------------------------------ instrumentation
     def profile_enable(self, on: bool = True):
         self._check(self._lib.solo_profile_enable(self._h, int(on)))

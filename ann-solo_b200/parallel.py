@@ -91,3 +91,49 @@ def allgather_topk(D: np.ndarray, I: np.ndarray, k: int):
     dist.all_gather(gD, tD)
     dist.all_gather(gI, tI)
     return merge_topk([t.cpu().numpy() for t in gD], [t.cpu().numpy() for t in gI], k)
+
+
+def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world: int = 1, group=None,
+                         peers=None) -> dict:
+    """Mode B for one batch: every GPU holds the whole query batch and a shard of the inverted
+    lists (``SoloEngine.ivf_set_owned_lists``). Each GPU scans its lists (device top-k rows), the
+    rows are exchanged with ONE all-gather (NCCL over NVLink), every GPU merges and finishes
+    (precursor window, best match) its contiguous slice of the queries on the device. Returns the
+    slice's results (rows ``shard_bounds(nq, rank, world)``).
+
+    ``peers``: single-process variant used by the one-GPU test — a list of engines standing in for
+    the ranks (each owning some lists); the exchange is a concatenation instead of a collective.
+    """
+    import torch
+    dev = torch.device("cuda", eng.device)
+    nq = len(q["off"]) - 1
+    k = params.k
+    engines = peers if peers is not None else [eng]
+    parts_D, parts_I = [], []
+    for e in engines:
+        e.stage_queries(q)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        e.ivf_search_staged(charge, k, params.nprobe, I.data_ptr(), D.data_ptr())
+        e.synchronize()
+        parts_D.append(D)
+        parts_I.append(I)
+    if peers is not None:
+        all_D, all_I, parts = torch.stack(parts_D), torch.stack(parts_I), len(peers)
+    elif world > 1:
+        import torch.distributed as dist
+        all_D = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+        all_I = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_D, parts_D[0], group=group)
+        dist.all_gather_into_tensor(all_I, parts_I[0], group=group)
+        torch.cuda.synchronize(dev)
+        parts = world
+    else:
+        all_D, all_I, parts = parts_D[0][None], parts_I[0][None], 1
+    b, e_ = shard_bounds(nq, rank, world)
+    mD = torch.empty((e_ - b, k), dtype=torch.float32, device=dev)
+    mI = torch.empty((e_ - b, k), dtype=torch.int64, device=dev)
+    eng.merge_topk_device(all_D.data_ptr(), all_I.data_ptr(), parts, nq, k, b, e_ - b, mD.data_ptr(), mI.data_ptr())
+    eng.score_staged_ids(charge, params, mI.data_ptr(), b, e_ - b)
+    res = eng.fetch_results()
+    return {key: v[b:e_] for key, v in res.items()}, (mD, mI)

@@ -39,6 +39,9 @@ OPEN_TOL, OPEN_MODE, FRAG_TOL = 500.0, "Da", 0.02
 TRAIN_ITERS = 2
 
 
+_emit = print
+
+
 def log(*a):
     if int(os.environ.get("RANK", "0")) == 0:
         print("[bench]", *a, file=sys.stderr, flush=True)
@@ -188,13 +191,20 @@ def run_solo(args, wl, rank, world, local_rank):
         for _ in range(warmup):
             step_fn()
         barrier()
-        if profile:
-            eng.profile_reset()
-            eng.profile_enable(True)
-        launches0 = eng.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ncu = profile and os.environ.get("SOLO_NCU") == "1"  # ncu --profile-from-start off
         with ClockSampler(local_rank) as clk:
+            # nvidia-smi polls every 200 ms and the K timed steps may be shorter than that: keep the GPU
+            # under the same load for about a second first so that samples are taken under load
+            t_load = time.time()
+            while not ncu and time.time() - t_load < 1.0:
+                step_fn()
+                torch.cuda.synchronize()
+            barrier()
+            if profile:
+                eng.profile_reset()
+                eng.profile_enable(True)
+            launches0 = eng.kernel_launches()
             if ncu:
                 torch.cuda.profiler.start()
             e0.record()
@@ -274,7 +284,8 @@ def run_solo(args, wl, rank, world, local_rank):
                 "share_of_step": round(scan["ms"] / ms_res, 4)}
     stages = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
 
-    cpu = cpu_baseline(wl, per_charge, q_by_charge, eng) if not args.no_cpu_baseline else None
+    # the CPU baseline is reported by the single-GPU run only (torchrun also pins OMP_NUM_THREADS=1)
+    cpu = cpu_baseline(wl, per_charge, q_by_charge, eng) if (not args.no_cpu_baseline and world == 1) else None
     line = {
         "metric": "query spectra/sec, cascade open search", "value": round(value, 1), "unit": "spectra/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3),
@@ -288,7 +299,7 @@ def run_solo(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stages,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def cpu_pipeline(o, store, q, cent, assign, nlist, wl, charge, threads, use_ref):
@@ -377,7 +388,7 @@ def run_reference(args, wl, rank, world):
     v = round(n / dt, 2)
     desc = {"value": v, "unit": "spectra/s", "cores": threads, "kind": "reference" if use_ref else "port",
             "sample": f"{n // args.steps} queries per step (bounded sample of the {wl['nq']}-query batch)"}
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "query spectra/sec, cascade open search", "value": v, "unit": "spectra/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
@@ -385,7 +396,7 @@ def run_reference(args, wl, rank, world):
                    "open_window": f"{OPEN_TOL} {OPEN_MODE}", "fragment_tol": FRAG_TOL},
         "cpu_baseline": desc,
         "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
 
 
 def main():
@@ -401,6 +412,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:

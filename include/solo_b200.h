@@ -157,6 +157,26 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
                       const double *q_prec_mz, int nq, int32_t *best_row, double *best_score,
                       int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand);
 
+/* ---- mode B: inverted lists sharded over GPUs ---------------------
+ * The reference has no multi-GPU path; these entry points are what a one-process-per-GPU driver
+ * needs around its collective (NCCL all-gather of the per-GPU top-k rows). All pointers named d_*
+ * are DEVICE pointers (e.g. torch tensors); the calls are asynchronous on the handle's stream. */
+/* owned[l] != 0: list l is stored on this GPU; the other lists stay empty here (every GPU adds
+ * the whole library, row ids stay global). NULL restores "all lists". */
+int solo_ivf_set_owned_lists(solo_handle *h, int charge, const uint8_t *owned, int nlist);
+/* Vectorise the staged query batch and search this GPU's lists: d_I (nq,k) int64 / d_D (nq,k)
+ * float32, sorted (score desc, id asc), padded with -1 / -inf. */
+int solo_ivf_search_staged(solo_handle *h, int charge, int k, int nprobe, int64_t *d_I, float *d_D);
+/* Merge `parts` such results, laid out (parts, nq, k) as all_gather_into_tensor leaves them, for the
+ * queries [q_begin, q_begin + nq_out): d_D/d_I (nq_out, k), same order and padding. */
+int solo_merge_topk_device(solo_handle *h, const float *d_D_parts, const int64_t *d_I_parts, int parts, int nq, int k,
+                           int q_begin, int nq_out, float *d_D, int64_t *d_I);
+/* Finish the staged batch's queries [q_begin, q_begin + nq_slice) from given top-k ids d_I
+ * (nq_slice, p->k): precursor window AND valid, then the best match; results land in the rows
+ * [q_begin, ...) that solo_fetch_results returns. */
+int solo_score_staged_ids(solo_handle *h, int charge, const solo_search_params *p, const int64_t *d_I, int q_begin,
+                          int nq_slice);
+
 /* ---- instrumentation ------------------------------------------------------------------
  * Per-stage device times (CUDA events on the launching stream) accumulated since the last
  * reset, and the number of kernels this library launched. Stage names: solo_stage_name(i). */

@@ -82,7 +82,12 @@ def _p(a, t):
 
 
 def num_threads() -> int:
-    return int(port().oracle_num_threads())
+    """Host threads the CPU baseline uses: every core this process may run on (torchrun pins
+    OMP_NUM_THREADS=1 for its workers, which would misreport the box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return int(port().oracle_num_threads())
 
 
 # ---------------------------------------------------------------- vectorisation (A2)
