@@ -204,13 +204,15 @@ struct TileCursor {
     const TcItem *items;
     int n_items, stride;
     int item, qb, nqb;
+    int bm;  // queries per tile (128; 256 for CTA pairs)
     TcItem cur, nxt;
     bool valid;
     __device__ __forceinline__ void load_next() {
         const int ni = item + stride;
         if (ni < n_items) nxt = items[ni];
     }
-    __device__ __forceinline__ void init(const TcItem *it, int n, int first, int step) {
+    __device__ __forceinline__ void init(const TcItem *it, int n, int first, int step, int tile_m = TC_BM) {
+        bm = tile_m;
         items = it;
         n_items = n;
         stride = step;
@@ -218,7 +220,7 @@ struct TileCursor {
         qb = 0;
         valid = item < n_items;
         if (valid) cur = items[item];
-        nqb = valid ? (cur.G + TC_BM - 1) / TC_BM : 0;
+        nqb = valid ? (cur.G + bm - 1) / bm : 0;
         load_next();
     }
     __device__ __forceinline__ bool first_qb() const { return qb == 0; }
@@ -229,7 +231,7 @@ struct TileCursor {
         item += stride;
         valid = item < n_items;
         cur = nxt;
-        nqb = (cur.G + TC_BM - 1) / TC_BM;
+        nqb = (cur.G + bm - 1) / bm;
         if (valid) load_next();
     }
 };
@@ -583,6 +585,360 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     }
 }
 
+
+// ======================================================================= CTA-pair variant (cta_group::2)
+//
+// Two CTAs of a cluster (one TPC) share every work item: the pair's tile is 256 queries (each CTA
+// gathers and drains its own 128) and the list chunk is split between them (CTA r keeps rows
+// [r N/2, (r+1) N/2) resident), so the resident chunk costs half the shared memory per CTA and the
+// ring of query stages — what hides the gather's L2 latency — roughly doubles. Only the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 (M = 256); its commits are multicast to both CTAs'
+// barriers. Cross-CTA signals: both CTAs' TMA loads complete on the leader's full_b; the peer's
+// MMA warp relays "my query stage is full" to the leader's full_peer; the peer's epilogue warps
+// arrive on the leader's tmem_empty.
+
+struct __align__(8) Tc2Barriers {
+    unsigned long long full_a[TC_MAX_STAGES];
+    unsigned long long full_peer[TC_MAX_STAGES];
+    unsigned long long empty_a[TC_MAX_STAGES];
+    unsigned long long full_b[TC_MAX_KB];
+    unsigned long long empty_b[TC_MAX_KB];
+    unsigned long long tmem_full[2];
+    unsigned long long tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+constexpr int TC2_BOX = 16;  // rows per TMA box of the pair kernel's tensor map
+
+template <int NUM_KB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    const int num_kb = NUM_KB > 0 ? NUM_KB : (a.dim + TC_BK - 1) / TC_BK;
+    const int half_nb = a.nb / 2;             // list rows resident in this CTA
+    const int b_kb_bytes = half_nb * 128;
+    const int n_stages = a.stages;
+    unsigned char *sA = tc_smem;
+    unsigned char *sB = tc_smem + n_stages * TC_A_BYTES;
+    Tc2Barriers *bars = reinterpret_cast<Tc2Barriers *>(sB + (size_t)num_kb * b_kb_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_items = (int)a.item_off[a.nlist];
+    const int first_item = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+    constexpr int BM2 = 2 * TC_BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_MAX_STAGES; ++s) {
+            mbar_init(smem_u32(&bars->full_a[s]), TC_PRODUCERS);
+            mbar_init(smem_u32(&bars->full_peer[s]), 1);
+            mbar_init(smem_u32(&bars->empty_a[s]), 1);
+        }
+        for (int kb = 0; kb < TC_MAX_KB; ++kb) {
+            mbar_init(smem_u32(&bars->full_b[kb]), 1);
+            mbar_init(smem_u32(&bars->empty_b[kb]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bars->tmem_full[b]), 1);
+            mbar_init(smem_u32(&bars->tmem_empty[b]), 8);  // four epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();  // barriers of both CTAs exist before any remote signal
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp < TC_EPI_WARPS) {
+        // ================= epilogue (this CTA's 128 query rows of every 256-query tile) =================
+        const int set = warp >> 2;
+        uint32_t unit = (uint32_t)set;
+        const int row = (int)rank * TC_BM + (warp & 3) * 32 + lane;  // row inside the 256-query tile
+        const float scale = 1.f / a.inv_scale;
+        TileCursor tc;
+        tc.init(a.items, n_items, first_item, item_step, BM2);
+        if (set == 1 && tc.valid) tc.advance();
+        int q = -1;
+        float thr = INFINITY;
+        if (tc.valid) {
+            const int gi = tc.qb * BM2 + row;
+            q = gi < tc.cur.G ? a.gq[tc.cur.g0 + gi] : -1;
+            if (q >= 0) thr = a.tau[q] * scale;
+        }
+        const uint32_t leader_empty0 = map_to_cta(smem_u32(&bars->tmem_empty[0]), 0);
+        const uint32_t leader_empty1 = map_to_cta(smem_u32(&bars->tmem_empty[1]), 0);
+        while (tc.valid) {
+            const TcItem it = tc.cur;
+            TileCursor nx = tc;
+            nx.advance();
+            if (nx.valid) nx.advance();
+            int q_next = -1;
+            if (nx.valid) {
+                const int gi = nx.qb * BM2 + row;
+                q_next = gi < nx.cur.G ? a.gq[nx.cur.g0 + gi] : -1;
+            }
+            const int buf = set;
+            mbar_wait(smem_u32(&bars->tmem_full[buf]), (unit >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * 256);
+            for (int c0 = 0; c0 < it.nv; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(tbase + (uint32_t)c0, r);
+                tc_wait_ld();
+                if (c0 + 32 >= it.nv) {  // last chunk of this accumulator: hand the buffer back to the leader's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(buf ? leader_empty1 : leader_empty0);
+                }
+                if (q < 0) continue;
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (__uint_as_float(r[j]) >= thr) mask |= 1u << j;
+                const int left = it.nv - c0;
+                if (left < 32) mask &= (1u << left) - 1u;
+                if (mask) {
+                    int slot = atomicAdd(&a.cnt[q], __popc(mask));
+                    unsigned long long *qbuf = a.buf + (int64_t)q * a.cap;
+                    const uint32_t pbase = (uint32_t)(it.p0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((mask >> j) & 1u) {
+                            if (slot < a.cap)
+                                qbuf[slot] = ((unsigned long long)__float_as_uint(__uint_as_float(r[j]) * a.inv_scale) << 32) |
+                                             (unsigned long long)(pbase + j);
+                            ++slot;
+                        }
+                    }
+                }
+            }
+            q = q_next;
+            thr = q >= 0 ? a.tau[q] * scale : INFINITY;
+            tc = nx;
+            unit += 2;
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ================= TMA: this CTA's half of the item's list chunk =================
+        uint32_t n_local = 0;
+        TcItem it, nxt;
+        int item = first_item;
+        if (item < n_items) it = a.items[item];
+        for (; item < n_items; item += item_step, ++n_local) {
+            if (item + item_step < n_items) nxt = a.items[item + item_step];
+            const int npad = (it.nv + 15) & ~15;         // MMA N
+            const int half = npad >> 1;                   // rows per CTA
+            const int nbox = (half + TC2_BOX - 1) / TC2_BOX;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(smem_u32(&bars->empty_b[kb]), (n_local & 1) ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = map_to_cta(smem_u32(&bars->full_b[kb]), 0);  // the leader's barrier
+                    if (leader) mbar_expect_tx(smem_u32(&bars->full_b[kb]), (uint32_t)(2 * nbox * TC2_BOX * 128));
+                    for (int j = 0; j < nbox; ++j)
+                        tma_load_2d_pair(smem_u32(sB + (size_t)kb * b_kb_bytes + j * TC2_BOX * 128), &tmap_vec, kb * TC_BK,
+                                         it.p0 + (int)rank * half + j * TC2_BOX, fb);
+                }
+                __syncwarp();
+            }
+            it = nxt;
+        }
+    } else if (warp == TC_EPI_WARPS + 1) {
+        uint32_t stage = 0, phase = 0, unit = 0, n_local = 0;
+        TileCursor tc;
+        tc.init(a.items, n_items, first_item, item_step, BM2);
+        if (leader) {
+            // ================= MMA issuer (leader CTA) =================
+            const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
+            while (tc.valid) {
+                const int npad = (tc.cur.nv + 15) & ~15;
+                // instruction descriptor: D=f32, A=B=f16, K-major, M=256 (pair), N=npad
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+                const int buf = unit & 1;
+                mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((unit >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+                const bool first_qb = tc.first_qb(), last_qb = tc.last_qb();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb]), n_local & 1);
+                    mbar_wait(smem_u32(&bars->full_a[stage]), phase);
+                    mbar_wait(smem_u32(&bars->full_peer[stage]), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        uint64_t adesc = desc_hi | (uint64_t)(((a_base + stage * TC_A_BYTES) >> 4) & 0x3FFFu);
+                        uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                        const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                        tc_mma_f16_pair(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                        for (int k = 1; k < ksteps; ++k) {
+                            adesc += 2;
+                            bdesc += 2;
+                            tc_mma_f16_pair(tmem_d, adesc, bdesc, idesc, 1u);
+                        }
+                        tc_commit_pair(smem_u32(&bars->empty_a[stage]));
+                        if (last_qb) tc_commit_pair(smem_u32(&bars->empty_b[kb]));
+                        if (kb == num_kb - 1) tc_commit_pair(smem_u32(&bars->tmem_full[buf]));
+                    }
+                    __syncwarp();
+                    if (++stage == (uint32_t)n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (last_qb) ++n_local;
+                ++unit;
+                tc.advance();
+            }
+        } else {
+            // ================= relay (peer CTA): "my query stage is full" -> the leader's full_peer =================
+            while (tc.valid) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bars->full_a[stage]), phase);
+                    if (elect_one()) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->full_peer[stage]), 0));
+                    __syncwarp();
+                    if (++stage == (uint32_t)n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc.advance();
+            }
+        }
+    } else {
+        // ================= A producers: this CTA's 128 query rows per k-block =================
+        const int p = threadIdx.x - (TC_EPI_WARPS + 2) * 32;
+        const int chunk = p & 7;
+        const int rbase = p >> 3;
+        constexpr int RSTEP = TC_PRODUCERS / 8;
+        constexpr int NR = TC_BM / RSTEP;
+        const uint32_t dst_off = (uint32_t)(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));
+        const uint32_t a_base = smem_u32(sA);
+        uint32_t stage = 0, phase = 0;
+        const size_t row_bytes = (size_t)a.dim * sizeof(__half);
+        const unsigned char *qh_c = reinterpret_cast<const unsigned char *>(a.qh) + chunk * 16;
+        const int row0 = (int)rank * TC_BM + rbase;
+        TileCursor tc;
+        tc.init(a.items, n_items, first_item, item_step, BM2);
+        const unsigned char *src[NR];
+        uint32_t nz[NR];
+        int qn[NR];
+        if (tc.valid) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int gi = row0 + RSTEP * i;
+                const bool real = gi < tc.cur.G;
+                const int q = a.gq[tc.cur.g0 + (real ? gi : 0)];
+                src[i] = qh_c + (size_t)q * row_bytes;
+                nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;
+            }
+        }
+        while (tc.valid) {
+            TileCursor nx = tc;
+            nx.advance();
+            const unsigned char *src_n[NR];
+            uint32_t nz_n[NR];
+            auto produce = [&](int kb) {
+                if (kb == 0 && nx.valid) {
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int gi = nx.qb * BM2 + row0 + RSTEP * i;
+                        const bool real = gi < nx.cur.G;
+                        const int q = a.gq[nx.cur.g0 + (real ? gi : 0)];
+                        qn[i] = real ? q : -1 - q;
+                    }
+                }
+                if (kb == num_kb / 2 && nx.valid) {
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const bool real = qn[i] >= 0;
+                        const int q = real ? qn[i] : -1 - qn[i];
+                        src_n[i] = qh_c + (size_t)q * row_bytes;
+                        nz_n[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;
+                    }
+                }
+                mbar_wait(smem_u32(&bars->empty_a[stage]), phase ^ 1u);
+                const uint32_t dst0 = a_base + stage * TC_A_BYTES + dst_off;
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
+                cp_async_arrive_noinc(smem_u32(&bars->full_a[stage]));
+                if (++stage == (uint32_t)n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            };
+            if (NUM_KB > 0) {
+#pragma unroll
+                for (int kb = 0; kb < NUM_KB; ++kb) produce(kb);
+            } else {
+                for (int kb = 0; kb < num_kb; ++kb) produce(kb);
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                src[i] = src_n[i];
+                nz[i] = nz_n[i];
+            }
+            tc = nx;
+        }
+        cp_async_wait<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory and barriers stay alive until the leader's last MMA retired
+    if (warp == TC_EPI_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
 __global__ void tc_item_count_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off, int nlist,
                                      int nb, int32_t *__restrict__ cnt) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -661,11 +1017,11 @@ static PFN_encodeTiled get_encode_fn() {
 
 bool tc_scan_supported(const IvfIndex &ix) { return ix.dim % 16 == 0 && ix.dim >= 16; }
 
-static bool tc_encode_rows(void *storage, const void *base, int dim, int64_t rows) {
+static bool tc_encode_rows(void *storage, const void *base, int dim, int64_t rows, int box_rows = TC_BOX) {
     CUtensorMap *m = reinterpret_cast<CUtensorMap *>(storage);
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)dim * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BOX};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -680,6 +1036,7 @@ void tc_make_tensor_map(IvfIndex &ix) {
     if (!tc_scan_supported(ix) || ix.nstored == 0) return;
     static_assert(sizeof(CUtensorMap) <= sizeof(ix.tmap_storage), "tensor map storage too small");
     ix.tmap_valid = tc_encode_rows(ix.tmap_storage, ix.vec_h.p, ix.dim, ix.nstored);
+    tc_encode_rows(ix.tmap16_storage, ix.vec_h.p, ix.dim, ix.nstored, TC2_BOX);  // CTA-pair kernel: 16-row boxes
 }
 
 // the same for the fp16 centroid table; called from ivf_set_centroids
@@ -748,13 +1105,27 @@ void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int 
     h->launches++;
 }
 
+// CTA-pair plan: each CTA keeps half of the chunk resident
+static void tc2_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out) {
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(Tc2Barriers) - 64;
+    static const int env_nb = getenv("SOLO_TC2_NB") ? atoi(getenv("SOLO_TC2_NB")) : 0;
+    int nb = env_nb >= 32 ? env_nb / 32 * 32 : 128;  // chunk rows per pair (multiple of 32: 16-row boxes per CTA)
+    while (nb > 32 && (avail - num_kb * (nb / 2) * 128) / TC_A_BYTES < 4) nb -= 32;
+    *nb_out = nb;
+    *stages_out = std::min((avail - num_kb * (nb / 2) * 128) / TC_A_BYTES, TC_MAX_STAGES);
+}
+
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
                     const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
                     int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
     SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
     const int nlist = ix.nlist;
     int nb, stages;
-    tc_smem_plan(ix, &nb, &stages);
+    static const bool env_pairs = getenv("SOLO_TC_PAIRS") && atoi(getenv("SOLO_TC_PAIRS")) != 0;
+    const bool pairs = h->opt_scan_pairs || env_pairs;
+    if (pairs) tc2_smem_plan(ix, &nb, &stages);
+    else tc_smem_plan(ix, &nb, &stages);
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     item_cnt.ensure((size_t)nlist * sizeof(int32_t));
     item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
@@ -786,6 +1157,19 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     static const int v_debug = getenv("SOLO_TC_DEBUG") ? atoi(getenv("SOLO_TC_DEBUG")) : 0;
     a.debug = v_debug;
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    if (pairs) {
+        const size_t smem2 = (size_t)stages * TC_A_BYTES + (size_t)num_kb * (nb / 2) * 128 + sizeof(Tc2Barriers) + 1024;
+        SOLO_REQUIRE(smem2 <= (size_t)TC_SMEM_MAX && stages >= 2, SOLO_ECAPACITY, "pair scan kernel needs %zu bytes of shared memory", smem2);
+        CUtensorMap map16;
+        memcpy(&map16, ix.tmap16_storage, sizeof map16);
+        auto kern2 = num_kb == 13 ? scan_tc2_kernel<13> : scan_tc2_kernel<0>;
+        SOLO_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        a.prof = nullptr;
+        kern2<<<kNumSMs, TC_THREADS, smem2, h->stream>>>(map16, a);  // 74 clusters of two CTAs
+        SOLO_CUDA(cudaGetLastError());
+        h->launches += 3;
+        return;
+    }
     const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
     SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
     CUtensorMap map;

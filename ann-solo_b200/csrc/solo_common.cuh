@@ -161,6 +161,7 @@ struct IvfIndex {
     // TMA descriptor (CUtensorMap, 128 bytes) of vec_h for the tcgen05 scan engine
     alignas(64) unsigned char tmap_storage[128];
     bool tmap_valid = false;
+    alignas(64) unsigned char tmap16_storage[128];     // vec_h again with 16-row boxes (CTA-pair scan kernel)
     alignas(64) unsigned char tmap_cent_storage[128];  // the same for cent_h (tensor-core coarse quantizer)
     bool tmap_cent_valid = false;
     int cent_scale_log2 = 10;  // cent_h holds centroid * 2^cent_scale_log2
@@ -178,6 +179,7 @@ struct solo_handle {
     int64_t launches = 0;
     bool profile = false;
     bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
+    bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
     int opt_round0_scores = 8192;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
     solo::StageProf prof[solo::ST_COUNT];
