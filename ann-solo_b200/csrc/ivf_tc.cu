@@ -166,6 +166,7 @@ struct TcScanArgs {
     int dim;
     int nb;                   // chunk capacity NB (multiple of 32)
     int stages;               // A stages in the ring
+    int kbb;                  // k-blocks per MMA issue batch
     float inv_scale;          // 2^-(scale_index + scale_query)
     const float *tau;         // [nq]
     unsigned long long *buf;  // [nq][cap]
@@ -429,7 +430,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         uint32_t stage = 0, phase = 0, unit = 0, n_local = 0;
+        unsigned long long pq0 = 0, pq1 = 0, pq2 = 0;
         bool ready = false;  // outcome of the early probe of full_a[stage]
+        uint32_t g = 0;      // running k-block counter (straight-line path)
+        const int kbb = max(1, min(a.kbb, n_stages / 2));  // k-blocks per issue batch
         const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
         TileCursor tc;
         tc.init(a.items, n_items, blockIdx.x, gridDim.x);
@@ -440,34 +444,112 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
             const bool first_qb = tc.first_qb(), last_qb = tc.last_qb();
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb]), n_local & 1, prof_on, pw1);
-                if (!ready) mbar_wait_prof(smem_u32(&bars->full_a[stage]), phase, prof_on, pw2);
-                // probe the next stage's barrier now; the answer is needed one k-block later
-                const uint32_t nstage = stage + 1 == (uint32_t)n_stages ? 0u : stage + 1;
-                const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
-                const bool ready_next = mbar_try_wait(smem_u32(&bars->full_a[nstage]), nphase);
-                tc_fence_after();
-                if (elect_one()) {
-                    uint64_t adesc = desc_hi | (uint64_t)(((a_base + stage * TC_A_BYTES) >> 4) & 0x3FFFu);
-                    uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
-                    const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
-                    if (!(a.debug & 16)) {
-                        tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-                        for (int k = 1; k < ksteps; ++k) {
-                            adesc += 2;  // 32 bytes (16 fp16 along K) inside the swizzle atom
-                            bdesc += 2;
-                            if (!(a.debug & 32)) tc_mma_f16(tmem_d, adesc, bdesc, idesc, 1u);
+            // k-blocks are issued in batches of KBB = 2: the first tcgen05.mma after a tcgen05.commit costs
+            // ~290 cycles of issue time (measured), the following ones ~15, so the commits of a batch go
+            // out together after its last MMA. This warp is the serial bottleneck of the kernel: with
+            // NUM_KB fixed and a four-stage ring everything below unrolls into straight-line code
+            // (stage = g & 3, phase = (g >> 2) & 1 for the running k-block counter g).
+            if (NUM_KB > 0 && n_stages == 4) {
+                constexpr int KBB = 2;
+                constexpr int NKB = NUM_KB > 0 ? NUM_KB : 1;
+#pragma unroll
+                for (int kb0 = 0; kb0 < NKB; kb0 += KBB) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int nkb = kb0 + KBB <= NKB ? KBB : NKB - kb0;
+#pragma unroll
+                    for (int j = 0; j < KBB; ++j) {
+                        if (j < nkb) {
+                            const uint32_t gj = g + (uint32_t)j;
+                            if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb0 + j]), n_local & 1);
+                            if (j > 0 || !ready) mbar_wait(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u);
                         }
                     }
-                    tc_commit(smem_u32(&bars->empty_a[stage]));  // frees the A stage when these MMAs retire
-                    if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb]));  // last reader of this B slot
-                    if (kb == num_kb - 1) tc_commit(smem_u32(&bars->tmem_full[buf]));
+                    const uint32_t gn = g + (uint32_t)nkb;
+                    const bool ready_next = mbar_try_wait(smem_u32(&bars->full_a[gn & 3u]), (gn >> 2) & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < KBB; ++j) {
+                            if (j < nkb) {
+                                const int kb = kb0 + j;
+                                const uint32_t st = (g + (uint32_t)j) & 3u;
+                                uint64_t adesc = desc_hi | (uint64_t)(((a_base + st * TC_A_BYTES) >> 4) & 0x3FFFu);
+                                uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                                const int ksteps = kb == NKB - 1 ? last_ksteps : TC_BK / 16;
+                                tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                                for (int k = 1; k < ksteps; ++k) {
+                                    adesc += 2;  // 32 bytes (16 fp16 along K) inside the swizzle atom
+                                    bdesc += 2;
+                                    tc_mma_f16(tmem_d, adesc, bdesc, idesc, 1u);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < KBB; ++j) {
+                            if (j < nkb) {
+                                tc_commit(smem_u32(&bars->empty_a[(g + (uint32_t)j) & 3u]));  // frees the A stage when the batch retires
+                                if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));    // last reader of this B slot
+                            }
+                        }
+                        if (kb0 + nkb == NKB) tc_commit(smem_u32(&bars->tmem_full[buf]));
+                    }
+                    __syncwarp();
+                    g = gn;
+                    ready = ready_next;
+                }
+                stage = g & 3u;
+                phase = (g >> 2) & 1u;
+            } else {
+            for (int kb0 = 0; kb0 < num_kb; kb0 += kbb) {
+                const int nkb = min(kbb, num_kb - kb0);
+                bool ready_next;
+                {
+                    uint32_t st = stage, ph = phase;
+                    for (int j = 0; j < nkb; ++j) {
+                        if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb0 + j]), n_local & 1, prof_on, pw1);
+                        if (j > 0 || !ready) mbar_wait_prof(smem_u32(&bars->full_a[st]), ph, prof_on, pw2);
+                        if (++st == (uint32_t)n_stages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    // probe the next batch's first stage now; the answer is needed one batch later
+                    ready_next = mbar_try_wait(smem_u32(&bars->full_a[st]), ph);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                    uint32_t st = stage;
+                    for (int j = 0; j < nkb; ++j) {
+                        const int kb = kb0 + j;
+                        uint64_t adesc = desc_hi | (uint64_t)(((a_base + st * TC_A_BYTES) >> 4) & 0x3FFFu);
+                        uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                        const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                        tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                        for (int k = 1; k < ksteps; ++k) {
+                            adesc += 2;
+                            bdesc += 2;
+                            tc_mma_f16(tmem_d, adesc, bdesc, idesc, 1u);
+                        }
+                        if (++st == (uint32_t)n_stages) st = 0;
+                    }
+                    st = stage;
+                    for (int j = 0; j < nkb; ++j) {
+                        tc_commit(smem_u32(&bars->empty_a[st]));
+                        if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));
+                        if (++st == (uint32_t)n_stages) st = 0;
+                    }
+                    if (kb0 + nkb == num_kb) tc_commit(smem_u32(&bars->tmem_full[buf]));
                 }
                 __syncwarp();
-                stage = nstage;
-                phase = nphase;
+                for (int j = 0; j < nkb; ++j)
+                    if (++stage == (uint32_t)n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 ready = ready_next;
+            }
+            g = 0;  // unused on this path
             }
             if (last_qb) ++n_local;
             ++unit;
@@ -477,6 +559,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
             a.prof[blockIdx.x * 8 + 2] = pw0;  // MMA: wait tmem_empty
             a.prof[blockIdx.x * 8 + 3] = pw1;  // MMA: wait full_b
             a.prof[blockIdx.x * 8 + 4] = pw2;  // MMA: wait full_a
+        }
+        if (prof_on) {  // the elected lane's issue-side breakdown (debug: reuses the TMA / producer slots)
+            pq0 = __reduce_max_sync(0xffffffffu, (unsigned)(pq0 >> 10));
+            pq1 = __reduce_max_sync(0xffffffffu, (unsigned)(pq1 >> 10));
+            pq2 = __reduce_max_sync(0xffffffffu, (unsigned)(pq2 >> 10));
+            if (lane == 0 && (a.debug & 64)) {
+                a.prof[blockIdx.x * 8 + 1] = pq0 << 10;
+                a.prof[blockIdx.x * 8 + 5] = pq1 << 10;
+                a.prof[blockIdx.x * 8 + 6] = pq2 << 10;
+            }
         }
     } else {
         // ================= A producers: gather 128 query rows per k-block =================
@@ -1146,6 +1238,7 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     a.dim = ix.dim;
     a.nb = nb;
     a.stages = stages;
+    { static const int env_kbb = getenv("SOLO_TC_KBB") ? atoi(getenv("SOLO_TC_KBB")) : 2; a.kbb = env_kbb; }
     a.inv_scale = ldexpf(1.f, -(ix.scale_log2 + q_scale_log2));
     a.tau = tau;
     a.buf = buf;
@@ -1224,6 +1317,7 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     a.dim = ix.dim;
     a.nb = nb;
     a.stages = stages;
+    { static const int env_kbb = getenv("SOLO_TC_KBB") ? atoi(getenv("SOLO_TC_KBB")) : 2; a.kbb = env_kbb; }
     a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
     a.dense_out = out;
     a.dense_ld = ld;

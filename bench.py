@@ -280,8 +280,15 @@ def run_solo(args, wl, rank, world, local_rank):
     scan_ms_per_launch = scan["ms"] / max(scan["launches"], 1)
     flops_per_launch = scan["units"] / max(scan["launches"], 1)
     achieved = flops_per_launch / (scan_ms_per_launch * 1e-3) / 1e12 if scan_ms_per_launch > 0 else 0.0
+    # DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(
+            "k3_list_scan_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     roofline = {"kernel": "k3_list_scan", "bound": "tensor", "achieved": round(achieved, 3), "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 5), "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 5), "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": round(scan_ms_per_launch, 4), "launches": scan["launches"],
                 "share_of_step": round(scan["ms"] / ms_res, 4)}
     stages = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
