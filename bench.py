@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (n_targets, decoy_fraction, queries per rank, nlist, nprobe, k, cpu sample queries)
-    "c2": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=512,
+    "c2": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=6144,
                label="C2: 16,384 queries vs 3M-vector library (2M targets + 1M decoys), charges 2-4"),
     "c2s": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=4096, nprobe=1024, k=1024, cpu_sample=128,
                 label="C2 (second point, nlist 4096)"),
@@ -434,7 +434,7 @@ def run_reference(args, wl, rank, world):
         stores[z], cents[z] = store, cent
     log(f"CPU index build: {time.time() - t0:.1f}s")
     n_all = sum(len(q["prec_mz"]) for q in q_by_charge.values())
-    sample = max(32, wl["cpu_sample"] // 2)
+    sample = max(32, wl["cpu_sample"] // 4)
 
     def step(i):
         n = 0
