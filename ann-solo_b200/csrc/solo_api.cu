@@ -153,6 +153,70 @@ window_candidates_kernel(const double *__restrict__ q_prec_mz, const float *__re
     if (!ids && threadIdx.x == 0) counts[q] = (int)s_run;
 }
 
+// The same candidate sets from the m/z-sorted view of the library (built at load time): binary search
+// of a slightly widened m/z interval, then the exact reference predicate on the rows inside it.
+// O(log N + rows in the window) per query instead of O(N): what the level-1 'std' search (a few ppm)
+// needs. Candidates come out in m/z order; the scorer breaks score ties by library row.
+__global__ void __launch_bounds__(128)
+window_candidates_sorted_kernel(const double *__restrict__ q_prec_mz, const float *__restrict__ sorted_mz32,
+                                const int32_t *__restrict__ sorted_row, const uint8_t *__restrict__ lib_valid,
+                                int64_t n_lib, int charge, double tol, int mode, int32_t *__restrict__ counts,
+                                const int64_t *__restrict__ off, int32_t *__restrict__ ids) {
+    __shared__ int s_n;
+    __shared__ int64_t s_lo, s_hi;
+    const int q = blockIdx.x;
+    const double qm = q_prec_mz[q];
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        double lo_mz, hi_mz;
+        if (mode == SOLO_TOL_DA) {
+            const double w = charge != 0 ? tol / fabs((double)charge) : INFINITY;
+            lo_mz = qm - w;
+            hi_mz = qm + w;
+        } else {
+            const double t = tol * 1e-6;
+            lo_mz = qm / (1.0 + t);
+            hi_mz = t < 1.0 ? qm / (1.0 - t) : INFINITY;
+        }
+        // widen: the exact predicate below decides, the interval only has to contain every passing row
+        lo_mz = lo_mz - 1e-6 - 1e-9 * fabs(lo_mz);
+        hi_mz = hi_mz + 1e-6 + 1e-9 * fabs(hi_mz);
+        if (!(lo_mz == lo_mz) || !(hi_mz == hi_mz)) {  // NaN query: scan everything, the predicate rejects
+            lo_mz = -INFINITY;
+            hi_mz = INFINITY;
+        }
+        int64_t a = 0, b = n_lib;  // first row with mz >= lo_mz
+        while (a < b) {
+            const int64_t m = (a + b) >> 1;
+            if ((double)sorted_mz32[m] < lo_mz) a = m + 1;
+            else b = m;
+        }
+        s_lo = a;
+        b = n_lib;  // first row with mz > hi_mz
+        while (a < b) {
+            const int64_t m = (a + b) >> 1;
+            if ((double)sorted_mz32[m] <= hi_mz) a = m + 1;
+            else b = m;
+        }
+        s_hi = a;
+    }
+    __syncthreads();
+    const int64_t lo = s_lo, hi = s_hi;
+    int mine = 0;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+        const int row = sorted_row[p];
+        if (lib_valid[row] && window_ok(qm, sorted_mz32[p], charge, tol, mode)) {
+            if (ids) ids[off[q] + atomicAdd(&s_n, 1)] = row;
+            else ++mine;
+        }
+    }
+    if (!ids) {
+        if (mine) atomicAdd(&s_n, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) counts[q] = s_n;
+    }
+}
+
 }  // namespace solo
 
 // ================================================================ C-ABI
@@ -205,7 +269,7 @@ void solo_destroy(solo_handle *h) {
     rel(h->lut);
     for (auto &kv : h->libs) {
         LibraryStore &L = kv.second;
-        rel(L.mz); rel(L.inten); rel(L.chg); rel(L.off); rel(L.prec_mz); rel(L.prec_mz32); rel(L.prec_z); rel(L.valid); rel(L.meta); rel(L.table);
+        rel(L.mz); rel(L.inten); rel(L.chg); rel(L.off); rel(L.prec_mz); rel(L.prec_mz32); rel(L.prec_z); rel(L.valid); rel(L.meta); rel(L.table); rel(L.sorted_mz32); rel(L.sorted_row);
     }
     for (auto &kv : h->ivf) {
         IvfIndex &x = kv.second;
@@ -363,6 +427,21 @@ int solo_load_library(solo_handle *h, int charge, const float *mz, const float *
             SOLO_CUDA(cudaMemsetAsync(L.valid.p, 1, std::max<int64_t>(n, 16), h->stream));
         }
         k5_build_aux(h, L);
+        {   // m/z-sorted view for the brute-force candidate search (NaN precursors sort last and never match)
+            std::vector<int32_t> order(n);
+            for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+                const float fx = prec_mz32[x], fy = prec_mz32[y];
+                if (fx != fx) return false;
+                if (fy != fy) return true;
+                return fx < fy;
+            });
+            std::vector<float> smz(n);
+            for (int64_t i = 0; i < n; ++i) smz[i] = prec_mz32[order[i]];
+            h2d(h, L.sorted_mz32, smz.data(), n * 4);
+            h2d(h, L.sorted_row, order.data(), n * 4);
+            SOLO_CUDA(cudaStreamSynchronize(h->stream));  // the vectors above go out of scope
+        }
         SOLO_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
@@ -745,18 +824,31 @@ int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p) 
             int64_t total = 0;
             {
                 StageTimer t(h, ST_CANDIDATES, 3);
-                window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
-                                                                    L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
-                                                                    p->tol_mode, h->r_n_cand.as<int32_t>(), nullptr, nullptr);
+                static const bool v_scan_all = getenv("SOLO_BF_SCAN_ALL") != nullptr;  // cross-check: the O(N) kernel
+                if (v_scan_all)
+                    window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
+                                                                        L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
+                                                                        p->tol_mode, h->r_n_cand.as<int32_t>(), nullptr, nullptr);
+                else
+                    window_candidates_sorted_kernel<<<nq, 128, 0, h->stream>>>(
+                        h->q_prec_mz.as<double>(), L.sorted_mz32.as<float>(), L.sorted_row.as<int32_t>(),
+                        L.valid.as<uint8_t>(), L.n, charge, p->tol_value, p->tol_mode, h->r_n_cand.as<int32_t>(), nullptr,
+                        nullptr);
                 SOLO_CUDA(cudaGetLastError());
                 // offsets = exclusive scan of the counts (single-CTA scan kernel lives in ivf.cu)
                 scan_counts_i32(h, h->r_n_cand.as<int32_t>(), nq, coff.as<int64_t>());
                 SOLO_CUDA(cudaMemcpyAsync(&total, coff.as<int64_t>() + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
                 SOLO_CUDA(cudaStreamSynchronize(h->stream));
                 cids.ensure(std::max<int64_t>(total, 1) * sizeof(int32_t));
-                window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
-                                                                    L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
-                                                                    p->tol_mode, nullptr, coff.as<int64_t>(), cids.as<int32_t>());
+                if (v_scan_all)
+                    window_candidates_kernel<<<nq, 256, 0, h->stream>>>(h->q_prec_mz.as<double>(), L.prec_mz32.as<float>(),
+                                                                        L.valid.as<uint8_t>(), L.n, charge, p->tol_value,
+                                                                        p->tol_mode, nullptr, coff.as<int64_t>(), cids.as<int32_t>());
+                else
+                    window_candidates_sorted_kernel<<<nq, 128, 0, h->stream>>>(
+                        h->q_prec_mz.as<double>(), L.sorted_mz32.as<float>(), L.sorted_row.as<int32_t>(),
+                        L.valid.as<uint8_t>(), L.n, charge, p->tol_value, p->tol_mode, nullptr, coff.as<int64_t>(),
+                        cids.as<int32_t>());
                 SOLO_CUDA(cudaGetLastError());
             }
             a.cand_ids = cids.as<int32_t>();

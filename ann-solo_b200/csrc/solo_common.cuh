@@ -122,6 +122,7 @@ struct LibraryStore {
     int64_t n_peaks = 0;
     int max_peaks = 0;
     DevBuf mz, inten, chg, off, prec_mz, prec_mz32, prec_z, valid;
+    DevBuf sorted_mz32, sorted_row;  // m/z-sorted view (float32 precursor m/z, library row) for window-only candidates
     DevBuf meta, table;  // scorer fast path: packed per-row metadata and m/z bucket tables (k5_build_aux)
 };
 

@@ -134,3 +134,40 @@ def test_spectral_library_dropin(engine, oracle, synth):
         sl.shutdown()
     finally:
         config.update(dict(num_list=256, num_probe=128, num_candidates=1024))
+
+
+@pytest.mark.parametrize("tol,tol_mode", [(0.5, "Da"), (20.0, "ppm"), (0.0, "Da"), (2.0e6, "ppm")])
+def test_window_only_candidates_at_the_boundaries(engine, oracle, synth, tol, tol_mode):
+    """Brute-force candidate sets (level-1 'std' search, --mode bf) from the m/z-sorted view: precursors
+    exactly on the window edge, duplicates, invalid rows and a NaN query must give the oracle's counts."""
+    from ann_solo_b200.engine import SoloEngine
+    charge = 2
+    lib = synth.make_library(1500, seed=71, decoy_seed=72)
+    store, _ = synth.split_by_charge(lib)[charge]
+    store = dict(store)
+    n = len(store["prec_mz"])
+    rng = np.random.default_rng(5)
+    store["prec_mz"] = store["prec_mz"].copy()
+    store["prec_mz"][:50] = 700.0                      # duplicates
+    store["prec_mz"][50:60] = np.float64(np.float32(700.25))   # exactly tol / charge away for the Da case
+    store["valid"] = store["valid"].copy()
+    store["valid"][rng.integers(0, n, 100)] = 0
+    queries = synth.make_queries(lib, 200, seed=73)
+    q = synth.take_spectra(queries, np.flatnonzero(queries["prec_z"] == charge))
+    q["prec_mz"] = q["prec_mz"].copy()
+    q["prec_mz"][0] = 700.0
+    q["prec_mz"][1] = 700.0 + 0.25
+    q["prec_mz"][2] = 700.0 * (1 + 20e-6)
+    q["prec_mz"][3] = np.nan
+    q["prec_mz"][4] = 1.0e9
+    engine.load_library(charge, store)
+    p = SoloEngine.make_params(False, 64, 6, tol, tol_mode, 0.02, True, max_pairs=50)
+    res = engine.search_batch(charge, p, q)
+    cand, coff = oracle.candidates(q["prec_mz"], store["prec_mz"].astype(np.float32), store["valid"], charge, tol, tol_mode)
+    assert np.array_equal(res["n_cand"], np.diff(coff))
+    bp, bs, npairs, pairs = oracle.best_match_batch(q, store, cand, coff, 0.02, True, sort_mode=1)
+    has = bp >= 0
+    row = np.full(len(bp), -1, np.int32)
+    row[has] = cand[coff[:-1][has] + bp[has]]
+    assert np.array_equal(res["best_row"], row)
+    assert np.array_equal(res["score"][has], bs[has])
