@@ -1416,7 +1416,8 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
                (sorted_out ? (size_t)IVF_MAX_K * sizeof(unsigned long long) : 0);
     };
     const int scap_thr = (int)std::min<int64_t>(cap, std::max<int64_t>(c0, a.k));   // round 0 appends <= c0 per query
-    const int scap_fin = std::min(cap, 8192);
+    static const int env_scap = getenv("SOLO_K4_SCAP") ? atoi(getenv("SOLO_K4_SCAP")) : 12288;
+    const int scap_fin = std::min(cap, std::max(1024, env_scap));
     const size_t tk_smem = tk_bytes(cap);
     SOLO_CUDA(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));

@@ -181,7 +181,7 @@ struct solo_handle {
     bool profile = false;
     bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
-    int opt_round0_scores = 8192;   // scores per query appended unconditionally by the first scan round
+    int opt_round0_scores = 4096;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
     solo::StageProf prof[solo::ST_COUNT];
 
