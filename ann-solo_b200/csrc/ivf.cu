@@ -390,7 +390,8 @@ struct SelectArgs {
 };
 
 __global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a) {
-    extern __shared__ uint32_t s_keys[];  // [nlist]
+    extern __shared__ __align__(16) uint32_t s_sel_keys[];  // [nlist]
+    uint32_t *s_keys = s_sel_keys;
     __shared__ uint32_t s_hist[KTH_BINS];
     __shared__ uint32_t s_bc[KTH_BC];
     __shared__ int s_cnt, s_eq_taken, s_back;
@@ -399,9 +400,33 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a
     int32_t *probes = a.probes;
     unsigned long long *probe_keys = a.probe_keys;
     const float *row = a.scores + (int64_t)q * a.pitch;
-    for (int i = threadIdx.x; i < nlist; i += blockDim.x) {
-        float s = row[i];
-        s_keys[i] = (s == s) ? ivf_f2o(s) : 0u;  // NaN -> lowest key
+    {   // all loads of a thread in flight together (the row pitch is a multiple of 32 floats: 16-byte aligned)
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        const int n4 = nlist >> 2;
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                v[u] = i < n4 ? row4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n4) {
+                    uint4 k;
+                    k.x = (v[u].x == v[u].x) ? ivf_f2o(v[u].x) : 0u;  // NaN -> lowest key
+                    k.y = (v[u].y == v[u].y) ? ivf_f2o(v[u].y) : 0u;
+                    k.z = (v[u].z == v[u].z) ? ivf_f2o(v[u].z) : 0u;
+                    k.w = (v[u].w == v[u].w) ? ivf_f2o(v[u].w) : 0u;
+                    reinterpret_cast<uint4 *>(s_keys)[i] = k;
+                }
+            }
+        }
+        for (int i = (n4 << 2) + threadIdx.x; i < nlist; i += blockDim.x) {
+            const float s = row[i];
+            s_keys[i] = (s == s) ? ivf_f2o(s) : 0u;
+        }
     }
     if (threadIdx.x == 0) {
         s_cnt = 0;
