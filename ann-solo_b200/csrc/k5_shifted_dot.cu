@@ -61,6 +61,77 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Overflow path: a (query, candidate) pair with more than K5_MAXM tentative peak matches (wide
+// fragment tolerances, dense spectra). The greedy assignment over the matches sorted by
+// (product desc, query peak asc, candidate peak asc) is the same as repeatedly taking the largest
+// remaining match whose two peaks are still free — so the matches are re-enumerated once per
+// accepted pair instead of being stored: no capacity, no scratch memory, exact. Warp-cooperative;
+// the candidate's peaks are in `c_mz / c_int / c_chg` (shared memory), the query's peaks are read
+// through `qmz(i) / qint(i)`, the mass shift of shift s is md_of_shift[s] (shared memory). Returns the score; pairs go to `cur_pairs`, *np_out their count.
+template <typename QMz, typename QInt>
+__device__ double k5_greedy_by_reselection(const double *c_mz, const float *c_int, const uint8_t *c_chg, int n, int nqp,
+                                           int nshift, const double *md_of_shift, double tol, QMz qmz, QInt qint,
+                                           uint16_t *cur_pairs, int *np_out) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long qu[2] = {0ull, 0ull}, cu[2] = {0ull, 0ull};  // used peaks (<= 128 each)
+    double score = 0.0;
+    int np = 0;
+    const int max_np = min(nqp, n);
+    const int W = nshift * nqp;
+    while (np < max_np) {
+        unsigned long long best = 0ull;
+        for (int w = lane; w < W; w += 32) {
+            const int s = w / nqp, i = w - s * nqp;
+            if ((qu[i >> 6] >> (i & 63)) & 1ull) continue;
+            const double md = md_of_shift[s];
+            const double qm = qmz(i);
+            const double thr = __dsub_rn(qm, tol);
+            int lo = 0, hi = n - 1;  // SpectrumMatch.cpp:39-46 as a binary search (clamped to n - 1)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (thr > __dadd_rn(c_mz[mid], md)) lo = mid + 1;
+                else hi = mid;
+            }
+            for (int j = lo; j < n; ++j) {
+                const double d = fabs(__dsub_rn(qm, __dadd_rn(c_mz[j], md)));
+                if (!(d <= tol)) break;
+                if ((cu[j >> 6] >> (j & 63)) & 1ull) continue;
+                const int cz = c_chg[j];
+                double mult = 0.0;
+                if (s == 0) mult = 1.0;
+                else if (cz == s) mult = 1.0;
+                else if (cz == 0) mult = 2.0 / 3.0;
+                if (mult > 0.0) {
+                    const float prod = __double2float_rn(__dmul_rn(__dmul_rn(mult, (double)qint(i)), (double)c_int[j]));
+                    const unsigned long long key = ((unsigned long long)float_to_ordered(prod) << 32) |
+                                                   ((unsigned long long)(0xFFFFu - (unsigned)i) << 16) |
+                                                   (unsigned long long)(0xFFFFu - (unsigned)j);
+                    best = key > best ? key : best;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+            best = y > best ? y : best;
+        }
+        if (best == 0ull) break;
+        const int i = 0xFFFF - (int)((best >> 16) & 0xFFFFu);
+        const int j = 0xFFFF - (int)(best & 0xFFFFu);
+        score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(best >> 32)));
+        if (lane == 0) cur_pairs[np] = (uint16_t)((i << 8) | j);
+        ++np;
+        qu[i >> 6] |= 1ull << (i & 63);
+        cu[j >> 6] |= 1ull << (j & 63);
+    }
+    __syncwarp();
+    *np_out = np;
+    return score;
+}
+
 template <int PPL>
 struct K5WarpMem {
     static constexpr int MAXP = 32 * PPL;
@@ -72,6 +143,7 @@ struct K5WarpMem {
     uint8_t c_chg[MAXP];
     int count;
     int pad;
+    double md[8];  // mass shift per shift index (overflow path)
 };
 
 template <int PPL>
@@ -169,70 +241,76 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_best_match_kernel(K5Params p
             }
         }
         __syncwarp();
-        int M = wm.count;
-        if (M > K5_MAXM) {  // reported, never silently truncated
+        const int M = wm.count;
+        double score = 0.0;
+        int np = 0;
+        if (M > K5_MAXM) {
+            // more tentative matches than the on-chip list holds: exact greedy by re-enumeration (counted, never truncated)
             if (lane == 0) atomicAdd(p.overflow, 1);
-            M = K5_MAXM;
-        }
-
-        // rank sort, descending, in place (keys are unique up to exact duplicates, which are
-        // ordered by slot and are interchangeable for the greedy pass)
-        if (M > 1) {
-            unsigned long long mine[MAXR];
-            int rank[MAXR];
-            const int R = (M + 31) >> 5;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                int idx = lane + 32 * r;
-                mine[r] = (r < R && idx < M) ? wm.keys[idx] : 0ull;
-                rank[r] = 0;
-            }
-            for (int j = 0; j < M; ++j) {
-                const unsigned long long kj = wm.keys[j];
-#pragma unroll
+            if (lane < 8) wm.md[lane] = md_lane;
+            __syncwarp();
+            score = k5_greedy_by_reselection(
+                wm.c_mz, wm.c_int, wm.c_chg, n, nqp, nshift, wm.md, tol, [&](int i) { return (double)p.q_mz[qb + i]; },
+                [&](int i) { return p.q_int[qb + i]; }, wm.cur_pairs, &np);
+        } else {
+            // rank sort, descending, in place (keys are unique up to exact duplicates, which are
+            // ordered by slot and are interchangeable for the greedy pass)
+            if (M > 1) {
+                unsigned long long mine[MAXR];
+                int rank[MAXR];
+                const int R = (M + 31) >> 5;
+    #pragma unroll
                 for (int r = 0; r < MAXR; ++r) {
-                    if (r < R) {
-                        int idx = lane + 32 * r;
-                        rank[r] += (kj > mine[r]) || (kj == mine[r] && j < idx);
+                    int idx = lane + 32 * r;
+                    mine[r] = (r < R && idx < M) ? wm.keys[idx] : 0ull;
+                    rank[r] = 0;
+                }
+                for (int j = 0; j < M; ++j) {
+                    const unsigned long long kj = wm.keys[j];
+    #pragma unroll
+                    for (int r = 0; r < MAXR; ++r) {
+                        if (r < R) {
+                            int idx = lane + 32 * r;
+                            rank[r] += (kj > mine[r]) || (kj == mine[r] && j < idx);
+                        }
+                    }
+                }
+                __syncwarp();
+    #pragma unroll
+                for (int r = 0; r < MAXR; ++r) {
+                    int idx = lane + 32 * r;
+                    if (r < R && idx < M) wm.keys[rank[r]] = mine[r];
+                }
+                __syncwarp();
+            }
+
+            // greedy assignment (SpectrumMatch.cpp:95-111), warp-uniform
+            unsigned long long qu[NW], cu[NW];
+    #pragma unroll
+            for (int w = 0; w < NW; ++w) qu[w] = cu[w] = 0ull;
+            const int max_np = min(nqp, n);
+            for (int m = 0; m < M && np < max_np; ++m) {
+                const unsigned long long key = wm.keys[m];
+                const int i = 0xFFFF - (int)((key >> 16) & 0xFFFFu);
+                const int j = 0xFFFF - (int)(key & 0xFFFFu);
+                bool used = false;
+    #pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    if ((i >> 6) == w) used |= (qu[w] >> (i & 63)) & 1ull;
+                    if ((j >> 6) == w) used |= (cu[w] >> (j & 63)) & 1ull;
+                }
+                if (!used) {
+                    score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(key >> 32)));
+                    if (lane == 0) wm.cur_pairs[np] = (uint16_t)((i << 8) | j);
+                    ++np;
+    #pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        if ((i >> 6) == w) qu[w] |= 1ull << (i & 63);
+                        if ((j >> 6) == w) cu[w] |= 1ull << (j & 63);
                     }
                 }
             }
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                int idx = lane + 32 * r;
-                if (r < R && idx < M) wm.keys[rank[r]] = mine[r];
-            }
-            __syncwarp();
-        }
 
-        // greedy assignment (SpectrumMatch.cpp:95-111), warp-uniform
-        double score = 0.0;
-        int np = 0;
-        unsigned long long qu[NW], cu[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) qu[w] = cu[w] = 0ull;
-        const int max_np = min(nqp, n);
-        for (int m = 0; m < M && np < max_np; ++m) {
-            const unsigned long long key = wm.keys[m];
-            const int i = 0xFFFF - (int)((key >> 16) & 0xFFFFu);
-            const int j = 0xFFFF - (int)(key & 0xFFFFu);
-            bool used = false;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                if ((i >> 6) == w) used |= (qu[w] >> (i & 63)) & 1ull;
-                if ((j >> 6) == w) used |= (cu[w] >> (j & 63)) & 1ull;
-            }
-            if (!used) {
-                score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(key >> 32)));
-                if (lane == 0) wm.cur_pairs[np] = (uint16_t)((i << 8) | j);
-                ++np;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    if ((i >> 6) == w) qu[w] |= 1ull << (i & 63);
-                    if ((j >> 6) == w) cu[w] |= 1ull << (j & 63);
-                }
-            }
         }
 
         // SpectrumMatch.cpp:118 — first candidate, then strictly greater only
@@ -327,6 +405,7 @@ struct K5FastWarpMem {
     __align__(8) uint8_t table[K5_NBUCKET];
     int count;
     int pad;
+    double md[8];  // mass shift per shift index (overflow path)
 };
 
 __global__ void k5_build_meta_kernel(const int64_t *__restrict__ off, const double *__restrict__ prec_mz,
@@ -540,58 +619,64 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
             }
         }
         __syncwarp();
-        int M = wm.count;
-        if (M > K5_MAXM) {  // reported, never silently truncated
-            if (lane == 0) atomicAdd(p.overflow, 1);
-            M = K5_MAXM;
-        }
-
-        // rank sort, descending, in place
-        if (M > 1) {
-            unsigned long long mine[MAXR];
-            int rank[MAXR];
-            const int R = (M + 31) >> 5;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const int idx = lane + 32 * r;
-                mine[r] = (r < R && idx < M) ? wm.keys[idx] : 0ull;
-                rank[r] = 0;
-            }
-            for (int j = 0; j < M; ++j) {
-                const unsigned long long kj = wm.keys[j];
-#pragma unroll
-                for (int r = 0; r < MAXR; ++r) {
-                    if (r < R) {
-                        const int idx = lane + 32 * r;
-                        rank[r] += (kj > mine[r]) || (kj == mine[r] && j < idx);
-                    }
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const int idx = lane + 32 * r;
-                if (r < R && idx < M) wm.keys[rank[r]] = mine[r];
-            }
-            __syncwarp();
-        }
-
-        // greedy assignment (SpectrumMatch.cpp:95-111), warp-uniform
+        const int M = wm.count;
         double score = 0.0;
         int np = 0;
-        unsigned long long qu = 0ull, cu = 0ull;
-        const int max_np = min(nqp, n);
-        for (int m = 0; m < M && np < max_np; ++m) {
-            const unsigned long long key = wm.keys[m];
-            const int i = 0xFFFF - (int)((key >> 16) & 0xFFFFu);
-            const int j = 0xFFFF - (int)(key & 0xFFFFu);
-            if (!(((qu >> i) | (cu >> j)) & 1ull)) {
-                score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(key >> 32)));
-                if (lane == 0) wm.cur_pairs[np] = (uint16_t)((i << 8) | j);
-                ++np;
-                qu |= 1ull << i;
-                cu |= 1ull << j;
+        if (M > K5_MAXM) {
+            // more tentative matches than the on-chip list holds: exact greedy by re-enumeration (counted, never truncated)
+            if (lane == 0) atomicAdd(p.overflow, 1);
+            if (lane < 8) wm.md[lane] = md_lane;
+            __syncwarp();
+            score = k5_greedy_by_reselection(
+                wm.c_mz, wm.c_int, wm.c_chg, n, nqp, nshift, wm.md, tol, [&](int i) { return s_qmz[i]; },
+                [&](int i) { return s_qint[i]; }, wm.cur_pairs, &np);
+        } else {
+            // rank sort, descending, in place
+            if (M > 1) {
+                unsigned long long mine[MAXR];
+                int rank[MAXR];
+                const int R = (M + 31) >> 5;
+    #pragma unroll
+                for (int r = 0; r < MAXR; ++r) {
+                    const int idx = lane + 32 * r;
+                    mine[r] = (r < R && idx < M) ? wm.keys[idx] : 0ull;
+                    rank[r] = 0;
+                }
+                for (int j = 0; j < M; ++j) {
+                    const unsigned long long kj = wm.keys[j];
+    #pragma unroll
+                    for (int r = 0; r < MAXR; ++r) {
+                        if (r < R) {
+                            const int idx = lane + 32 * r;
+                            rank[r] += (kj > mine[r]) || (kj == mine[r] && j < idx);
+                        }
+                    }
+                }
+                __syncwarp();
+    #pragma unroll
+                for (int r = 0; r < MAXR; ++r) {
+                    const int idx = lane + 32 * r;
+                    if (r < R && idx < M) wm.keys[rank[r]] = mine[r];
+                }
+                __syncwarp();
             }
+
+            // greedy assignment (SpectrumMatch.cpp:95-111), warp-uniform
+            unsigned long long qu = 0ull, cu = 0ull;
+            const int max_np = min(nqp, n);
+            for (int m = 0; m < M && np < max_np; ++m) {
+                const unsigned long long key = wm.keys[m];
+                const int i = 0xFFFF - (int)((key >> 16) & 0xFFFFu);
+                const int j = 0xFFFF - (int)(key & 0xFFFFu);
+                if (!(((qu >> i) | (cu >> j)) & 1ull)) {
+                    score = __dadd_rn(score, (double)ordered_to_float((uint32_t)(key >> 32)));
+                    if (lane == 0) wm.cur_pairs[np] = (uint16_t)((i << 8) | j);
+                    ++np;
+                    qu |= 1ull << i;
+                    cu |= 1ull << j;
+                }
+            }
+
         }
 
         // SpectrumMatch.cpp:118 — first candidate, then strictly greater only

@@ -112,6 +112,7 @@ enum Stage {
 struct StageProf {
     double ms = 0.0;
     int64_t launches = 0;
+    int64_t k5_overflow_pairs = 0;  // (query, candidate) pairs with > 256 tentative matches seen so far
     double units = 0.0;  // stage-specific unit count (bytes or flops), summed
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
@@ -178,6 +179,7 @@ struct solo_handle {
     cudaStream_t stream = nullptr;
     std::string last_error;
     int64_t launches = 0;
+    int64_t k5_overflow_pairs = 0;  // (query, candidate) pairs with > 256 tentative matches seen so far
     bool profile = false;
     bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan

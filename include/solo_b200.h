@@ -26,7 +26,7 @@ enum {
     SOLO_ECUDA = -2,     /* CUDA runtime / driver error */
     SOLO_ENOMEM = -3,    /* device allocation failed */
     SOLO_ESTATE = -4,    /* call order (e.g. search before a library/index is loaded) */
-    SOLO_ECAPACITY = -5  /* a fixed on-chip capacity was exceeded (reported, never truncated) */
+    SOLO_ECAPACITY = -5  /* a fixed capacity was exceeded (reported, never truncated) */
 };
 
 enum { SOLO_TOL_DA = 0, SOLO_TOL_PPM = 1 };

@@ -96,6 +96,33 @@ def test_more_than_64_peaks_path(engine, oracle):
         assert np.array_equal(got[3][i, :got[2][i]], want[3][i, :want[2][i]])
 
 
+@pytest.mark.parametrize("npk", [48, 110])
+def test_more_tentative_matches_than_the_on_chip_list(engine, oracle, npk):
+    """Dense spectra and a wide fragment tolerance: far more than 256 tentative matches per pair. The
+    kernels switch to the exact greedy-by-re-enumeration path (no truncation, no error); both the
+    <= 64-peak fast kernel and the general kernel are covered."""
+    rng = np.random.default_rng(9)
+    def spec(prec, z):
+        mz = np.sort(rng.uniform(300, 330, npk)).astype(np.float32)
+        it = (rng.random(npk) + 0.05).astype(np.float32)
+        return dict(prec=prec, z=z, mz=mz.tolist(), I=(it / np.linalg.norm(it)).tolist(),
+                    chg=rng.integers(0, 3, npk).tolist())
+    cands = [spec(500 + 3.1 * i, 2) for i in range(12)]
+    qs = [spec(503.0, 2), spec(520.0, 2), spec(500.0, 2)]
+    q, lib = _store(qs), _store(cands)
+    engine.load_library(CH, lib)
+    ids = np.tile(np.arange(12, dtype=np.int32), 3)
+    off = np.array([0, 12, 24, 36], np.int64)
+    for shift in (False, True):
+        got = engine.best_match_batch(CH, q, ids, off, 5.0, shift, max_pairs=128)
+        want = oracle.best_match_batch(q, lib, ids, off, 5.0, shift, sort_mode=1, max_pairs=128)
+        assert np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1], want[1])
+        assert np.array_equal(got[2], want[2]) and got[2].min() > npk // 2
+        for i in range(3):
+            assert np.array_equal(got[3][i, :got[2][i]], want[3][i, :want[2][i]])
+
+
 def test_capacity_errors_are_loud(engine):
     from ann_solo_b200 import SoloError
     big = dict(prec=500.0, z=2, mz=np.linspace(100, 900, 129).tolist(), I=[0.1] * 129)
