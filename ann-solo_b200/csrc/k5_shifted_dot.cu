@@ -455,6 +455,7 @@ struct K5FastParams {
     K5Params p;
     const LibMeta *meta;
     const uint8_t *table;
+    int debug;  // timing experiments only (SOLO_K5_DEBUG): 1 = skip the match passes, 2 = skip sort + greedy
 };
 
 __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams fp) {
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
         const int nshift = (p.allow_shift && fabs(delta) >= tol) ? z + 1 : 1;
         const double md_lane = (lane > 0 && lane < nshift) ? __ddiv_rn(delta, (double)lane) : 0.0;
 
-        if (n > 0) {
+        if (n > 0 && !(fp.debug & 1)) {
             const int W = nshift * nqp;
             const float inv_nqp = 1.0f / (float)nqp;
             for (int w0 = 0; w0 < W; w0 += 32) {
@@ -593,11 +594,14 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
                     // (float rounding at m/z 2000 is 1.2e-4, far inside the 0.004 margin)
                     int b = __float2int_rd((__double2float_rn(__dsub_rn(thr, md)) - 0.004f) * (1.0f / K5_BUCKET_MZ));
                     b = max(0, min(K5_NBUCKET - 1, b));
-                    int lo = wm.table[b];
-                    lo = min(lo, n - 1);
-                    while (lo < n - 1 && thr > __dadd_rn(wm.c_mz[lo], md)) ++lo;  // SpectrumMatch.cpp:39-46
-                    for (int j = lo; j < n; ++j) {
-                        const double d = fabs(__dsub_rn(qm, __dadd_rn(wm.c_mz[j], md)));
+                    int j = min((int)wm.table[b], n - 1);
+                    double x = __dadd_rn(wm.c_mz[j], md);  // candidate peak m/z + mass shift, reused by the match test
+                    while (j < n - 1 && thr > x) {          // SpectrumMatch.cpp:39-46 (at most a few steps from the bucket start)
+                        ++j;
+                        x = __dadd_rn(wm.c_mz[j], md);
+                    }
+                    for (;;) {
+                        const double d = fabs(__dsub_rn(qm, x));
                         if (!(d <= tol)) break;
                         const int cz = wm.c_chg[j];
                         double mult = 0.0;
@@ -614,12 +618,14 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
                                                 (unsigned long long)(0xFFFFu - (unsigned)j);
                             }
                         }
+                        if (++j >= n) break;
+                        x = __dadd_rn(wm.c_mz[j], md);
                     }
                 }
             }
         }
         __syncwarp();
-        const int M = wm.count;
+        const int M = (fp.debug & 2) ? 0 : wm.count;
         double score = 0.0;
         int np = 0;
         if (M > K5_MAXM) {
@@ -789,6 +795,8 @@ void launch_best_match(solo_handle *h, const ScoreArgs &a) {
         fp.p = p;
         fp.meta = L.meta.as<LibMeta>();
         fp.table = L.table.as<uint8_t>();
+        static const int v_dbg = getenv("SOLO_K5_DEBUG") ? atoi(getenv("SOLO_K5_DEBUG")) : 0;
+        fp.debug = v_dbg;
         const size_t smem = sizeof(K5FastWarpMem) * K5_WARPS;
         SOLO_CUDA(cudaFuncSetAttribute(k5_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k5_fast_kernel<<<a.nq, K5_WARPS * 32, smem, h->stream>>>(fp);
