@@ -405,7 +405,8 @@ struct K5FastWarpMem {
     __align__(8) uint8_t table[K5_NBUCKET];
     int count;
     int pad;
-    double md[8];  // mass shift per shift index (overflow path)
+    double md[8];  // mass shift per shift index
+    float mdf[8];  // ... as float (bucket lookup only)
 };
 
 __global__ void k5_build_meta_kernel(const int64_t *__restrict__ off, const double *__restrict__ prec_mz,
@@ -463,6 +464,8 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
     extern __shared__ __align__(16) unsigned char k5_smem[];
     K5FastWarpMem *wm_all = reinterpret_cast<K5FastWarpMem *>(k5_smem);
     __shared__ double s_qmz[64];
+    __shared__ double s_qthr[64];  // q_mz - tol (SpectrumMatch.cpp:41)
+    __shared__ float s_qtf[64];    // float copy of it minus the bucket safety margin
     __shared__ float s_qint[64];
     __shared__ double s_best_score[K5_WARPS];
     __shared__ int s_best_pos[K5_WARPS];
@@ -478,7 +481,10 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
     const double q_prec = p.q_prec_mz[q];
     const double tol = p.tol;
     for (int i = threadIdx.x; i < nqp; i += blockDim.x) {
-        s_qmz[i] = (double)p.q_mz[qb + i];
+        const double qm = (double)p.q_mz[qb + i];
+        s_qmz[i] = qm;
+        s_qthr[i] = __dsub_rn(qm, tol);
+        s_qtf[i] = __double2float_rn(__dsub_rn(qm, tol)) - 0.004f;
         s_qint[i] = p.q_int[qb + i];
     }
     __syncthreads();
@@ -576,6 +582,11 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
         const double delta = __dmul_rn(__dsub_rn(q_prec, c_prec), (double)z);
         const int nshift = (p.allow_shift && fabs(delta) >= tol) ? z + 1 : 1;
         const double md_lane = (lane > 0 && lane < nshift) ? __ddiv_rn(delta, (double)lane) : 0.0;
+        if (lane < 8) {
+            wm.md[lane] = md_lane;
+            wm.mdf[lane] = __double2float_rn(md_lane);
+        }
+        __syncwarp();
 
         if (n > 0 && !(fp.debug & 1)) {
             const int W = nshift * nqp;
@@ -586,13 +597,13 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
                 // w = s * nqp + i; exact for these small integers
                 const int s = active ? __float2int_rz(((float)w + 0.5f) * inv_nqp) : 0;
                 const int i = active ? w - s * nqp : 0;
-                const double md = __shfl_sync(0xffffffffu, md_lane, s);
                 if (active) {
+                    const double md = wm.md[s];
                     const double qm = s_qmz[i];
-                    const double thr = __dsub_rn(qm, tol);
+                    const double thr = s_qthr[i];
                     // bucket start: every peak below the bucket edge satisfies thr > c_mz + md with a wide margin
-                    // (float rounding at m/z 2000 is 1.2e-4, far inside the 0.004 margin)
-                    int b = __float2int_rd((__double2float_rn(__dsub_rn(thr, md)) - 0.004f) * (1.0f / K5_BUCKET_MZ));
+                    // (float rounding at m/z 2000 is 1.2e-4 per term, far inside the 0.004 margin)
+                    int b = __float2int_rd((s_qtf[i] - wm.mdf[s]) * (1.0f / K5_BUCKET_MZ));
                     b = max(0, min(K5_NBUCKET - 1, b));
                     int j = min((int)wm.table[b], n - 1);
                     double x = __dadd_rn(wm.c_mz[j], md);  // candidate peak m/z + mass shift, reused by the match test
@@ -631,8 +642,6 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
         if (M > K5_MAXM) {
             // more tentative matches than the on-chip list holds: exact greedy by re-enumeration (counted, never truncated)
             if (lane == 0) atomicAdd(p.overflow, 1);
-            if (lane < 8) wm.md[lane] = md_lane;
-            __syncwarp();
             score = k5_greedy_by_reselection(
                 wm.c_mz, wm.c_int, wm.c_chg, n, nqp, nshift, wm.md, tol, [&](int i) { return s_qmz[i]; },
                 [&](int i) { return s_qint[i]; }, wm.cur_pairs, &np);
