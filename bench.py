@@ -36,7 +36,7 @@ WORKLOADS = {
                  label="tiny smoke workload"),
 }
 OPEN_TOL, OPEN_MODE, FRAG_TOL = 500.0, "Da", 0.02
-TRAIN_ITERS = 2
+TRAIN_ITERS = int(os.environ.get("SOLO_TRAIN_ITERS", "2"))  # Lloyd iterations of the index build (not timed)
 
 
 _emit = print
@@ -139,6 +139,13 @@ def run_solo(args, wl, rank, world, local_rank):
         n_vec[z] = (len(store["prec_mz"]), nlist)
     eng.synchronize()
     log(f"index build (k-means {TRAIN_ITERS} it. + add, all charges): {time.time() - t0:.1f}s  {n_vec}")
+    if os.environ.get("SOLO_BENCH_STATS") == "1":
+        for z in charges:
+            a_ = eng.ivf_assignment(z)
+            sizes = np.bincount(a_[a_ >= 0], minlength=n_vec[z][1])
+            log(f"list sizes z={z}: mean {sizes.mean():.1f} p50 {np.percentile(sizes, 50):.0f} p90 {np.percentile(sizes, 90):.0f} "
+                f"max {sizes.max()} empty {(sizes == 0).sum()} frac>96 {(sizes > 96).mean():.3f} frac>192 {(sizes > 192).mean():.3f} "
+                f"chunks/list {np.ceil(sizes / 96).mean():.3f}")
 
     max_pairs = 50
     params = SoloEngine.make_params(True, wl["k"], wl["nprobe"], OPEN_TOL, OPEN_MODE, FRAG_TOL, True, max_pairs)
