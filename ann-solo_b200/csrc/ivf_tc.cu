@@ -167,6 +167,7 @@ struct TcScanArgs {
     int nb;                   // chunk capacity NB (multiple of 32)
     int stages;               // A stages in the ring
     int kbb;                  // k-blocks per MMA issue batch
+    int wide;                 // 1: list vectors are streamed per (tile, k-block) next to the query stage (chunks of up to 256 rows)
     float inv_scale;          // 2^-(scale_index + scale_query)
     const float *tau;         // [nq]
     unsigned long long *buf;  // [nq][cap]
@@ -256,7 +257,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     unsigned char *sA = tc_smem;
     const int n_stages = a.stages;
     unsigned char *sB = tc_smem + n_stages * TC_A_BYTES;
-    TcBarriers *bars = reinterpret_cast<TcBarriers *>(sB + (size_t)num_kb * b_kb_bytes);
+    // wide mode: one B buffer of nb rows per stage; resident mode: one per k-block
+    const bool wide = a.wide != 0;
+    TcBarriers *bars = reinterpret_cast<TcBarriers *>(sB + (size_t)(wide ? n_stages : num_kb) * b_kb_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = (int)a.item_off[a.nlist];
@@ -406,6 +409,33 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
         uint32_t n_local = 0;
         TcItem it, nxt;
         int item = blockIdx.x;
+        if (wide) {
+            // the chunk's k-block is loaded again for every query block, into the stage the gather fills
+            // (it comes from L2 after the first query block); full_b[stage] carries the transaction count
+            uint32_t stage = 0, phase = 0;
+            TileCursor tc;
+            tc.init(a.items, n_items, blockIdx.x, gridDim.x);
+            while (tc.valid) {
+                const int nbox = (tc.cur.nv + TC_BOX - 1) / TC_BOX;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_prof(smem_u32(&bars->empty_a[stage]), phase ^ 1u, prof_on, pw0);
+                    if (elect_one()) {
+                        const uint32_t fb = smem_u32(&bars->full_b[stage]);
+                        mbar_expect_tx(fb, (uint32_t)(nbox * TC_BOX * 128));
+                        for (int j = 0; j < nbox; ++j)
+                            tma_load_2d(smem_u32(sB + (size_t)stage * b_kb_bytes + j * TC_BOX * 128), &tmap_vec, kb * TC_BK,
+                                        tc.cur.p0 + j * TC_BOX, fb);
+                    }
+                    __syncwarp();
+                    if (++stage == (uint32_t)n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc.advance();
+            }
+            item = n_items;  // skip the resident-mode loop below
+        }
         if (item < n_items) it = a.items[item];
         for (; item < n_items; item += gridDim.x, ++n_local) {
             if (item + (int)gridDim.x < n_items) nxt = a.items[item + gridDim.x];
@@ -461,7 +491,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                     for (int j = 0; j < KBB; ++j) {
                         if (j < nkb) {
                             const uint32_t gj = g + (uint32_t)j;
-                            if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb0 + j]), n_local & 1);
+                            if (wide) mbar_wait(smem_u32(&bars->full_b[gj & 3u]), (gj >> 2) & 1u);
+                            else if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb0 + j]), n_local & 1);
                             if (j > 0 || !ready) mbar_wait(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u);
                         }
                     }
@@ -475,7 +506,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                                 const int kb = kb0 + j;
                                 const uint32_t st = (g + (uint32_t)j) & 3u;
                                 uint64_t adesc = desc_hi | (uint64_t)(((a_base + st * TC_A_BYTES) >> 4) & 0x3FFFu);
-                                uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                                uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (wide ? st : (uint32_t)kb) * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
                                 const int ksteps = kb == NKB - 1 ? last_ksteps : TC_BK / 16;
                                 tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
                                 for (int k = 1; k < ksteps; ++k) {
@@ -489,7 +520,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                         for (int j = 0; j < KBB; ++j) {
                             if (j < nkb) {
                                 tc_commit(smem_u32(&bars->empty_a[(g + (uint32_t)j) & 3u]));  // frees the A stage when the batch retires
-                                if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));    // last reader of this B slot
+                                if (last_qb && !wide) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));  // last reader of this B slot
                             }
                         }
                         if (kb0 + nkb == NKB) tc_commit(smem_u32(&bars->tmem_full[buf]));
@@ -507,7 +538,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                 {
                     uint32_t st = stage, ph = phase;
                     for (int j = 0; j < nkb; ++j) {
-                        if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb0 + j]), n_local & 1, prof_on, pw1);
+                        if (wide) mbar_wait_prof(smem_u32(&bars->full_b[st]), ph, prof_on, pw1);
+                        else if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb0 + j]), n_local & 1, prof_on, pw1);
                         if (j > 0 || !ready) mbar_wait_prof(smem_u32(&bars->full_a[st]), ph, prof_on, pw2);
                         if (++st == (uint32_t)n_stages) {
                             st = 0;
@@ -523,7 +555,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                     for (int j = 0; j < nkb; ++j) {
                         const int kb = kb0 + j;
                         uint64_t adesc = desc_hi | (uint64_t)(((a_base + st * TC_A_BYTES) >> 4) & 0x3FFFu);
-                        uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (uint32_t)kb * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
+                        uint64_t bdesc = desc_hi | (uint64_t)(((b_base + (wide ? st : (uint32_t)kb) * (uint32_t)b_kb_bytes) >> 4) & 0x3FFFu);
                         const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
                         tc_mma_f16(tmem_d, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
                         for (int k = 1; k < ksteps; ++k) {
@@ -536,7 +568,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                     st = stage;
                     for (int j = 0; j < nkb; ++j) {
                         tc_commit(smem_u32(&bars->empty_a[st]));
-                        if (last_qb) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));
+                        if (last_qb && !wide) tc_commit(smem_u32(&bars->empty_b[kb0 + j]));
                         if (++st == (uint32_t)n_stages) st = 0;
                     }
                     if (kb0 + nkb == num_kb) tc_commit(smem_u32(&bars->tmem_full[buf]));
@@ -1031,13 +1063,14 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
     }
 }
 
+// only lists with len_lo < length <= len_hi take part (the scan may split the lists between two kernel variants)
 __global__ void tc_item_count_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off, int nlist,
-                                     int nb, int32_t *__restrict__ cnt) {
+                                     int nb, int64_t len_lo, int64_t len_hi, int32_t *__restrict__ cnt) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     int64_t G = goff[l + 1] - goff[l];
     int64_t len = list_off[l + 1] - list_off[l];
-    cnt[l] = (len > 0 && G > 0) ? (int32_t)((len + nb - 1) / nb) : 0;
+    cnt[l] = (len > len_lo && len <= len_hi && G > 0) ? (int32_t)((len + nb - 1) / nb) : 0;
 }
 
 __global__ void tc_item_fill_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off,
@@ -1208,23 +1241,24 @@ static void tc2_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out) {
     *stages_out = std::min((avail - num_kb * (nb / 2) * 128) / TC_A_BYTES, TC_MAX_STAGES);
 }
 
-void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
-                    const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
-                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
-    SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
+static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
+                         const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
+                         int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items, bool pairs, bool wide, int64_t len_lo,
+                         int64_t len_hi) {
     const int nlist = ix.nlist;
     int nb, stages;
-    static const bool env_pairs = getenv("SOLO_TC_PAIRS") && atoi(getenv("SOLO_TC_PAIRS")) != 0;
-    const bool pairs = h->opt_scan_pairs || env_pairs;
     if (pairs) tc2_smem_plan(ix, &nb, &stages);
-    else tc_smem_plan(ix, &nb, &stages);
+    else if (wide) {
+        nb = 256;
+        stages = std::min((TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64) / (TC_A_BYTES + nb * 128), TC_MAX_STAGES);
+    } else tc_smem_plan(ix, &nb, &stages);
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     item_cnt.ensure((size_t)nlist * sizeof(int32_t));
     item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
     // every list contributes at most ceil(len / nb) <= len / nb + 1 items
     items.ensure((size_t)(ix.nstored / nb + nlist + 1) * sizeof(TcItem));
-    tc_item_count_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(), nlist, nb,
-                                                                    item_cnt.as<int32_t>());
+    tc_item_count_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(), nlist, nb, len_lo,
+                                                                    len_hi, item_cnt.as<int32_t>());
     scan_counts_i32(h, item_cnt.as<int32_t>(), nlist, item_off.as<int64_t>());
     tc_item_fill_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(),
                                                                    item_off.as<int64_t>(), nlist, nb, items.as<TcItem>());
@@ -1263,8 +1297,9 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
         h->launches += 3;
         return;
     }
-    const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
-    SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
+    const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)(wide ? stages : num_kb) * nb * 128 + sizeof(TcBarriers) + 1024;
+    SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX && stages >= 2, SOLO_ECAPACITY, "scan kernel needs %zu bytes of shared memory", smem);
+    a.wide = wide ? 1 : 0;
     CUtensorMap map;
     memcpy(&map, ix.tmap_storage, sizeof map);
     static const int v_epi2 = getenv("SOLO_TC_EPI2") ? 1 : 0;
@@ -1276,6 +1311,31 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     SOLO_CUDA(cudaGetLastError());
     h->launches += 3;
     tc_prof_report(h, "scan", kNumSMs);
+}
+
+// K3 for one round. Lists up to `hybrid` vectors go through the resident-chunk kernel (<= 96-row chunks,
+// read once per item), longer lists through the streamed-chunk variant (up to 256 rows per MMA, the
+// chunk re-read from L2 per query block): fewer, larger tiles where the issue-bound pipeline pays most.
+void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
+                    const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
+                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
+    SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
+    static const bool env_pairs = getenv("SOLO_TC_PAIRS") && atoi(getenv("SOLO_TC_PAIRS")) != 0;
+    const bool pairs = h->opt_scan_pairs || env_pairs;
+    static const int env_wide = getenv("SOLO_TC_WIDE") ? atoi(getenv("SOLO_TC_WIDE")) : -1;
+    const bool wide = !pairs && (env_wide >= 0 ? env_wide != 0 : h->opt_scan_wide);
+    static const int env_hybrid = getenv("SOLO_TC_HYBRID") ? atoi(getenv("SOLO_TC_HYBRID")) : -1;
+    const int64_t hybrid = env_hybrid >= 0 ? env_hybrid : h->opt_scan_hybrid;
+    const int64_t all = (int64_t)1 << 40;
+    if (pairs || wide || hybrid <= 0 || ix.max_list_len <= hybrid) {
+        scan_tc_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, pairs, wide, 0,
+                     all);
+        return;
+    }
+    scan_tc_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, false, false, 0,
+                 hybrid);
+    scan_tc_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, false, true,
+                 hybrid, all);
 }
 
 // K2 on the tensor cores: approximate scores of every query against every centroid,

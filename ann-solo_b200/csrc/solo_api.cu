@@ -304,6 +304,11 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
         } else if (strcmp(key, "round0_scores") == 0) {
             SOLO_REQUIRE(value >= 1024 && value <= 16384, SOLO_EINVAL, "round0_scores must be in [1024, 16384]");
             h->opt_round0_scores = (int)value;
+        } else if (strcmp(key, "scan_wide") == 0) {
+            h->opt_scan_wide = value != 0;
+        } else if (strcmp(key, "scan_hybrid") == 0) {
+            SOLO_REQUIRE(value >= 0 && value <= 12288, SOLO_EINVAL, "scan_hybrid must be in [0, 12288]");
+            h->opt_scan_hybrid = (int)value;
         } else if (strcmp(key, "scan_pairs") == 0) {
             h->opt_scan_pairs = value != 0;
         } else if (strcmp(key, "front_probes") == 0) {

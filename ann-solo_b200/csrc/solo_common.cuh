@@ -182,6 +182,8 @@ struct solo_handle {
     int64_t k5_overflow_pairs = 0;  // (query, candidate) pairs with > 256 tentative matches seen so far
     bool profile = false;
     bool opt_scan_exact = false;  // solo_set_option("scan_engine", 1): CUDA-core exact list scan
+    bool opt_scan_wide = false;   // solo_set_option("scan_wide", 1): list vectors streamed per tile, chunks of up to 256 rows
+    int opt_scan_hybrid = 0;      // > 0: lists longer than this use the streamed-chunk scan variant
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
     int opt_round0_scores = 4096;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
