@@ -29,6 +29,13 @@ class SearchParams(C.Structure):
                 ("mz_is_f64", C.c_int32), ("max_pairs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class IdxannInfo(C.Structure):
+    _fields_ = [("d", C.c_int32), ("metric", C.c_int32), ("is_trained", C.c_int32), ("reserved", C.c_int32),
+                ("ntotal", C.c_int64), ("nlist", C.c_int64), ("nprobe", C.c_int64), ("code_size", C.c_int64),
+                ("nstored", C.c_int64), ("max_list_len", C.c_int64), ("bytes_parsed", C.c_int64),
+                ("fourcc", C.c_char * 8), ("quantizer_fourcc", C.c_char * 8)]
+
+
 # every symbol include/solo_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SYMBOLS = {
@@ -55,6 +62,11 @@ SYMBOLS = {
     "solo_ivf_search": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "solo_debug_scan_dump": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_i32), _vp, _vp]),
     "solo_ivf_coarse": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "solo_idxann_inspect": (C.c_int, [C.c_char_p, _vp, C.c_char_p, C.c_int]),
+    "solo_ivf_read_index": (C.c_int, [_vp, C.c_int, C.c_char_p, C.POINTER(_i64)]),
+    "solo_ivf_write_index": (C.c_int, [_vp, C.c_int, C.c_char_p, _i64]),
+    "solo_ivf_add_assigned": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int, _vp]),
+    "solo_ivf_reconstruct": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp]),
     "solo_best_match_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _f64, C.c_int,
                                         C.c_int, _vp, _vp, _vp, _vp]),
     "solo_select_slot": (C.c_int, [_vp, C.c_int]),

@@ -79,5 +79,11 @@ void ivf_reset(IvfIndex &ix);
 void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a);
 void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
                uint64_t seed);
+// faiss_io.cu: Faiss ".idxann" files, explicit list assignment, dense read-back
+void ivf_add_assigned(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, const int32_t *list_of_row);
+void ivf_read_index(solo_handle *h, IvfIndex &ix, const char *path, int64_t *nprobe_out);
+void ivf_write_index(solo_handle *h, IvfIndex &ix, const char *path, int64_t nprobe);
+void ivf_reconstruct(solo_handle *h, IvfIndex &ix, int64_t row0, int64_t n, float *h_out);
+void idxann_inspect(const char *path, solo_idxann_info *info);
 
 }  // namespace solo

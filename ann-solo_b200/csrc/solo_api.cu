@@ -555,6 +555,45 @@ int solo_ivf_get_assignment(solo_handle *h, int charge, int32_t *list_of_row) {
     });
 }
 
+int solo_idxann_inspect(const char *path, solo_idxann_info *info, char *errbuf, int errbuf_len) {
+    if (errbuf && errbuf_len > 0) errbuf[0] = 0;
+    if (!path || !info) return SOLO_EINVAL;
+    try {
+        idxann_inspect(path, info);
+        return SOLO_OK;
+    } catch (const Error &e) {
+        if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", e.msg.c_str());
+        return e.code;
+    } catch (const std::exception &e) {
+        if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", e.what());
+        return SOLO_EINVAL;
+    }
+}
+
+int solo_ivf_read_index(solo_handle *h, int charge, const char *path, int64_t *nprobe) {
+    if (!h || !path) return SOLO_EINVAL;
+    return guarded(h, [&] { ivf_read_index(h, get_ivf(h, charge, false), path, nprobe); });
+}
+
+int solo_ivf_write_index(solo_handle *h, int charge, const char *path, int64_t nprobe) {
+    if (!h || !path) return SOLO_EINVAL;
+    return guarded(h, [&] { ivf_write_index(h, get_ivf(h, charge, true), path, nprobe); });
+}
+
+int solo_ivf_add_assigned(solo_handle *h, int charge, const float *x, int64_t n, int dim, const int32_t *list_of_row) {
+    if (!h || ((!x || !list_of_row) && n > 0)) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(dim == ix.dim, SOLO_EINVAL, "dim %d does not match the index (%d)", dim, ix.dim);
+        if (n > 0) ivf_add_assigned(h, ix, x, n, list_of_row);
+    });
+}
+
+int solo_ivf_reconstruct(solo_handle *h, int charge, int64_t row0, int64_t n, float *out) {
+    if (!h || (!out && n > 0)) return SOLO_EINVAL;
+    return guarded(h, [&] { ivf_reconstruct(h, get_ivf(h, charge, true), row0, n, out); });
+}
+
 int solo_ivf_search(solo_handle *h, int charge, const float *queries, int nq, int dim, int k, int nprobe, int64_t *I,
                     float *D) {
     if (!h || !queries || !I) return SOLO_EINVAL;

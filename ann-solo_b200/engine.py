@@ -147,6 +147,31 @@ class SoloEngine:
         self._check(self._lib.solo_ivf_get_assignment(self._h, int(charge), _ptr(out)))
         return out
 
+    def ivf_add_assigned(self, charge: int, x: np.ndarray, list_of_row: np.ndarray):
+        """add() with the inverted list of every row given by the caller (-1 = reserve the id only)."""
+        x = _c(x, np.float32)
+        lst = _c(list_of_row, np.int32)
+        if lst.shape != (x.shape[0],):
+            raise ValueError("list_of_row must have one entry per row")
+        self._check(self._lib.solo_ivf_add_assigned(self._h, int(charge), _ptr(x), x.shape[0], x.shape[1], _ptr(lst)))
+
+    def ivf_reconstruct(self, charge: int, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        ntotal, _, d = self.ivf_info(charge)
+        n = ntotal - row0 if n is None else n
+        out = np.empty((n, d), np.float32)
+        self._check(self._lib.solo_ivf_reconstruct(self._h, int(charge), int(row0), int(n), _ptr(out)))
+        return out
+
+    def ivf_write_index(self, charge: int, path: str, nprobe: int = 1):
+        """faiss.write_index (reference spectral_library.py:181)."""
+        self._check(self._lib.solo_ivf_write_index(self._h, int(charge), str(path).encode(), int(nprobe)))
+
+    def ivf_read_index(self, charge: int, path: str) -> int:
+        """faiss.read_index (reference spectral_library.py:490); returns the nprobe stored in the file."""
+        nprobe = C.c_int64()
+        self._check(self._lib.solo_ivf_read_index(self._h, int(charge), str(path).encode(), C.byref(nprobe)))
+        return nprobe.value
+
     def ivf_search(self, charge: int, queries: np.ndarray, k: int, nprobe: int, want_d: bool = True):
         q = _c(queries, np.float32)
         nq, d = q.shape

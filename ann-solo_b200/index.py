@@ -5,10 +5,12 @@ so parity runs can share centroids with the oracle.
 """
 from __future__ import annotations
 
+import ctypes as C
 import itertools
 
 import numpy as np
 
+from . import _lib
 from .spectrum import default_engine
 
 METRIC_INNER_PRODUCT = 0
@@ -62,3 +64,38 @@ class IndexIVFFlat:
 
     def setNumProbes(self, nprobe: int):  # GpuIndexIVF spelling used at spectral_library.py:495
         self.nprobe = int(nprobe)
+
+    def reconstruct_n(self, i0: int = 0, ni: int = None) -> np.ndarray:
+        return self._eng.ivf_reconstruct(self._slot, i0, ni)
+
+
+def write_index(index: IndexIVFFlat, fname: str) -> None:
+    """faiss.write_index (reference spectral_library.py:181): Faiss' IndexIVFFlat byte layout."""
+    if not index.is_trained:
+        raise RuntimeError("index is not trained")
+    index._eng.ivf_write_index(index._slot, fname, index.nprobe)
+
+
+def inspect_index(fname: str) -> dict:
+    """Header and list table of a Faiss IndexIVFFlat file, parsed on the host (no GPU needed)."""
+    info = _lib.IdxannInfo()
+    err = C.create_string_buffer(512)
+    rc = _lib.load().solo_idxann_inspect(str(fname).encode(), C.byref(info), err, len(err))
+    if rc != 0:
+        if rc == _lib.SOLO_EINVAL:
+            raise ValueError(err.value.decode())
+        raise _lib.SoloError(rc, err.value.decode())
+    out = {name: getattr(info, name) for name, _ in info._fields_ if name != "reserved"}
+    out["fourcc"] = info.fourcc.decode()
+    out["quantizer_fourcc"] = info.quantizer_fourcc.decode()
+    return out
+
+
+def read_index(fname: str, engine=None, slot=None) -> IndexIVFFlat:
+    """faiss.read_index (reference spectral_library.py:490): the file's centroids and inverted lists
+    are taken as stored (no re-training, no re-assignment)."""
+    info = inspect_index(fname)
+    index = IndexIVFFlat(IndexFlatIP(info["d"]), info["d"], info["nlist"], info["metric"], engine=engine, slot=slot)
+    index.nprobe = max(1, index._eng.ivf_read_index(index._slot, fname))
+    index.is_trained = True
+    return index

@@ -4,15 +4,18 @@ hot path: ``SpectralLibrary.search`` / ``_search_cascade`` / ``_search_batch`` /
 <= config.batch_size queries is ONE fused device call (vectorise -> IVF top-k -> precursor
 window -> shifted dot) instead of per-query Python/Faiss/Cython work.
 
-Out of scope here: file readers, HDF5/.spcfg caches, .idxann files, mokapot
-rescoring. The library is handed over as an object with the reader surface the hot path
+Out of scope here: file readers, HDF5/.spcfg caches, mokapot rescoring. ANN indexes
+are cached in Faiss' own ``.idxann`` files when ``ann_basename`` is given (reference :92-130). The library is handed over as an object with the reader surface the hot path
 uses (``spec_info`` and ``read_spectrum``); FDR scoring is an injectable callable.
 """
 from __future__ import annotations
 
 import collections
 import copy
+import hashlib
+import json
 import logging
+import os
 from typing import Callable, Dict, Iterator, List, Optional
 
 import numpy as np
@@ -92,7 +95,11 @@ class SpectralLibrary:
 
     def __init__(self, library, engine: Optional[SoloEngine] = None, device: int = 0,
                  centroids: Optional[Dict[int, np.ndarray]] = None,
-                 score_ssms: Callable = tdc_score_ssms, train_iters: int = 10) -> None:
+                 score_ssms: Callable = tdc_score_ssms, train_iters: int = 10,
+                 ann_basename: Optional[str] = None) -> None:
+        """``ann_basename``: what the reference derives from the library file name
+        (``os.path.splitext(filename)[0]``, :99-100); when given, the index of every charge is read
+        from / written to ``{ann_basename}_{hash[:7]}_{charge}.idxann`` like the reference does."""
         self._library_reader = library
         self._engine = engine or SoloEngine(device)
         self._score_ssms = score_ssms
@@ -100,6 +107,7 @@ class SpectralLibrary:
         self._num_candidates = config.num_candidates
         self._engine.set_vectorizer(config.min_mz, config.max_mz, config.bin_size, config.hash_len)
         self._ann_charges = set()
+        self._ann_filenames = {}
         self._lib_ids = {}
         for charge, info in self._library_reader.spec_info["charge"].items():
             self._engine.load_library(charge, self._charge_store(charge))
@@ -108,7 +116,26 @@ class SpectralLibrary:
             # No ANN index for infrequent precursor charges (reference :101-104).
             ann_charges = [z for z, info in self._library_reader.spec_info["charge"].items()
                            if len(info["id"]) >= config.num_list]
-            self._create_ann_indexes(sorted(ann_charges), centroids or {}, train_iters)
+            create_ann_charges = []
+            for charge in sorted(ann_charges):
+                if ann_basename is None:
+                    create_ann_charges.append(charge)
+                    continue
+                self._ann_filenames[charge] = (f"{ann_basename}_{self._get_hyperparameter_hash()[:7]}_"
+                                               f"{charge}.idxann")
+                if (getattr(self._library_reader, "is_recreated", False) or
+                        not os.path.isfile(self._ann_filenames[charge])):
+                    create_ann_charges.append(charge)
+                    logging.warning("Missing ANN index for charge %d", charge)
+                else:  # reference _get_ann_index :490 (loaded once: every charge stays resident in HBM)
+                    self._engine.ivf_read_index(charge, self._ann_filenames[charge])
+                    self._ann_charges.add(charge)
+            self._create_ann_indexes(create_ann_charges, centroids or {}, train_iters)
+
+    def _get_hyperparameter_hash(self) -> str:
+        """Reference :119-131."""
+        hyperparameters_bytes = json.dumps({hp: config[hp] for hp in self._hyperparameters}).encode("utf-8")
+        return hashlib.sha1(hyperparameters_bytes).hexdigest()
 
     def _charge_store(self, charge: int) -> dict:
         if hasattr(self._library_reader, "charge_store"):
@@ -131,6 +158,8 @@ class SpectralLibrary:
                 self._engine.ivf_train(charge, vecs[np.isfinite(vecs).all(axis=1)], config.num_list, train_iters)
             self._engine.ivf_add_library(charge)
             self._ann_charges.add(charge)
+            if charge in self._ann_filenames:  # reference :181
+                self._engine.ivf_write_index(charge, self._ann_filenames[charge])
 
     def shutdown(self) -> None:
         self._library_reader.close()

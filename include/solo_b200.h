@@ -104,6 +104,44 @@ int solo_debug_scan_dump(solo_handle *h, int charge, int nq, int32_t *cap, int32
 int solo_ivf_coarse(solo_handle *h, int charge, const float *queries, int nq, int dim, int nprobe,
                     int32_t *probes);
 
+/* ---- Faiss index files (".idxann") -----------------------------------------------------
+ * Replaces faiss.write_index(ann_index, filename) (spectral_library.py:181) and
+ * faiss.read_index(filename) (spectral_library.py:490) for the index type the reference builds:
+ * IndexIVFFlat over an IndexFlatIP quantizer, float32 codes, sequential ids. The byte layout is
+ * Faiss' own ("IwFl" / "IxFI" / "ilar"), so a file written here loads in Faiss and a file the
+ * reference wrote loads here with its trained centroids AND its list assignment untouched. */
+typedef struct solo_idxann_info {
+    int32_t d;             /* vector dimension (hash_len) */
+    int32_t metric;        /* 0 = inner product, 1 = L2 */
+    int32_t is_trained;
+    int32_t reserved;
+    int64_t ntotal;        /* ids run 0..ntotal-1 */
+    int64_t nlist;
+    int64_t nprobe;        /* value stored in the file (Faiss default 1; the reference sets it after loading) */
+    int64_t code_size;     /* bytes per stored row = 4 * d */
+    int64_t nstored;       /* sum of the list sizes */
+    int64_t max_list_len;
+    int64_t bytes_parsed;  /* == file size for a well-formed file */
+    char fourcc[8];            /* "IwFl" */
+    char quantizer_fourcc[8];  /* "IxFI" */
+} solo_idxann_info;
+/* Parse and validate the headers and list table of an index file on the host. Needs no handle and
+ * no GPU (it moves no vectors). */
+int solo_idxann_inspect(const char *path, solo_idxann_info *info, char *errbuf, int errbuf_len);
+/* faiss.read_index: replace the index of `charge` by the file's. *nprobe (may be NULL) receives the
+ * stored nprobe. SOLO_EINVAL for other index types, truncated files, non-sequential ids. */
+int solo_ivf_read_index(solo_handle *h, int charge, const char *path, int64_t *nprobe);
+/* faiss.write_index: `nprobe` is stored in the file's nprobe field (the reference writes the Faiss
+ * default, 1). Rows skipped by add() (NaN) keep their id but appear in no list. */
+int solo_ivf_write_index(solo_handle *h, int charge, const char *path, int64_t nprobe);
+/* add() with the inverted list of every row chosen by the caller (list_of_row[i] in [0, nlist), or
+ * -1 to reserve id i without storing the row) instead of the arg-max-centroid rule: what a Faiss
+ * file carries, and what mode B (lists sharded over GPUs) uses to replay one global assignment. */
+int solo_ivf_add_assigned(solo_handle *h, int charge, const float *x, int64_t n, int dim,
+                          const int32_t *list_of_row);
+/* index.reconstruct_n(row0, n): dense float32 copies of stored rows (skipped rows come back zero). */
+int solo_ivf_reconstruct(solo_handle *h, int charge, int64_t row0, int64_t n, float *out);
+
 /* ---- K5: (shifted) dot product, greedy peak assignment, best candidate ----------------
  * Replaces spectrum_match.pyx:28 get_best_match -> SpectrumMatch.cpp:8 SpectrumMatcher::dot,
  * batched over queries. Candidates are rows of the loaded library store of `charge`, given as
