@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsolo_b200.so")
 
 SOLO_OK, SOLO_EINVAL, SOLO_ECUDA, SOLO_ENOMEM, SOLO_ESTATE, SOLO_ECAPACITY = 0, -1, -2, -3, -4, -5
 TOL_DA, TOL_PPM = 0, 1
+N_SSM_FEATURES = 44
 
 
 class SoloError(RuntimeError):
@@ -75,6 +76,10 @@ SYMBOLS = {
     "solo_fetch_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "solo_search_batch": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "solo_ssm_feature_name": (C.c_char_p, [C.c_int]),
+    "solo_ssm_features": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int,
+                                    _vp, _vp]),
+    "solo_ssm_features_staged": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "solo_ivf_set_owned_lists": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "solo_ivf_search_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "solo_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

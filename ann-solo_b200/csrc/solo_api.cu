@@ -4,6 +4,7 @@
 #include <cmath>
 
 #include "ivf.cuh"
+#include "k6_ssm_features.cuh"
 #include "solo_common.cuh"
 
 using namespace solo;
@@ -933,6 +934,137 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
     rc = solo_search_staged(h, charge, p);
     if (rc) return rc;
     return solo_fetch_results(h, best_row, best_score, n_pairs, pairs, n_cand);
+}
+
+// ---- K6: SSM feature table ----------------------------------------------------------------
+static const char *kFeatureNames[SOLO_N_SSM_FEATURES] = {
+    "sequence_len", "precursor_charge_2", "precursor_charge_3", "precursor_charge_4", "precursor_charge_5",
+    "query_prec_mz", "lib_prec_mz", "mz_diff_ppm", "abs_mz_diff_ppm", "mz_diff_da", "abs_mz_diff_da", "cosine",
+    "cosine_top5", "n_matched_peaks", "frac_n_peaks_query", "frac_n_peaks_lib", "frac_n_peaks_lib_top5",
+    "frac_int_query", "frac_int_lib", "frac_int_lib_top5", "mse_mz", "mse_mz_top5", "mse_int", "mse_int_top5",
+    "contrast_angle", "contrast_angle_top5", "hypergeometric_score", "kendalltau", "ms_for_id_v1", "ms_for_id_v2",
+    "entropy_unweighted", "entropy_weighted", "scribe_fragment_acc", "scribe_fragment_acc_top5", "manhattan",
+    "euclidean", "chebyshev", "pearsonr", "pearsonr_top5", "spearmanr", "spearmanr_top5", "braycurtis", "canberra",
+    "ruzicka"};
+
+const char *solo_ssm_feature_name(int column) {
+    return column >= 0 && column < SOLO_N_SSM_FEATURES ? kFeatureNames[column] : "";
+}
+
+// device-side arguments are complete except out/bad; runs the kernel and copies the table to the host
+static void run_features(solo_handle *h, FeatureArgs &a, const int32_t *h_q_charge, const int32_t *h_seq_len,
+                         double *h_out) {
+    static_assert(SOLO_N_SSM_FEATURES == k6::N_FEATURES, "header and kernel disagree on the column count");
+    const int n = a.n;
+    if (n <= 0) return;
+    DevBuf &out = h->scratch[21], &zc = h->scratch[22], &sl = h->scratch[23], &bad = h->scratch[24];
+    out.ensure((size_t)n * k6::N_FEATURES * sizeof(double));
+    bad.ensure(sizeof(int32_t));
+    SOLO_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int32_t), h->stream));
+    a.q_charge = nullptr;
+    a.sequence_len = nullptr;
+    if (h_q_charge) {
+        h2d(h, zc, h_q_charge, (size_t)n * sizeof(int32_t));
+        a.q_charge = zc.as<int32_t>();
+    }
+    if (h_seq_len) {
+        h2d(h, sl, h_seq_len, (size_t)n * sizeof(int32_t));
+        a.sequence_len = sl.as<int32_t>();
+    }
+    a.n_peak_bins = h->n_bins;   // get_dim(config.min_mz, config.max_mz, config.bin_size) (utils.py:398-404)
+    a.out = out.as<double>();
+    a.bad = bad.as<int32_t>();
+    launch_ssm_features(h, a);
+    int32_t n_bad = 0;
+    SOLO_CUDA(cudaMemcpyAsync(&n_bad, bad.p, sizeof n_bad, cudaMemcpyDeviceToHost, h->stream));
+    SOLO_CUDA(cudaMemcpyAsync(h_out, out.p, (size_t)n * k6::N_FEATURES * sizeof(double), cudaMemcpyDeviceToHost,
+                              h->stream));
+    SOLO_CUDA(cudaStreamSynchronize(h->stream));
+    SOLO_REQUIRE(n_bad == 0, SOLO_ECAPACITY, "%d SSMs hold more than %d peaks or pairs beyond max_pairs", n_bad,
+                 k6::MAX_PEAKS);
+}
+
+static void fill_library(FeatureArgs &a, const LibraryStore &L) {
+    a.l_mz = L.mz.as<float>();
+    a.l_int = L.inten.as<float>();
+    a.l_off = L.off.as<int64_t>();
+    a.l_prec_mz = L.prec_mz.as<double>();
+}
+
+int solo_ssm_features(solo_handle *h, int charge, const void *q_mz, int q_mz_is_f64, const float *q_intensity,
+                      const int64_t *q_off, const double *q_prec_mz, const int32_t *q_prec_charge, int n_ssm,
+                      const int32_t *lib_row, const uint32_t *pairs, const int32_t *n_pairs, int max_pairs,
+                      const int32_t *sequence_len, double *out) {
+    if (!h || n_ssm < 0 || (n_ssm > 0 && (!q_mz || !q_intensity || !q_off || !q_prec_mz || !lib_row || !pairs ||
+                                          !n_pairs || !out)))
+        return SOLO_EINVAL;
+    return guarded(h, [&] {
+        if (n_ssm == 0) return;
+        LibraryStore &L = get_lib(h, charge);
+        SOLO_REQUIRE(max_pairs >= 1, SOLO_EINVAL, "max_pairs must be >= 1");
+        SOLO_REQUIRE(q_off[0] == 0, SOLO_EINVAL, "query offsets must start at 0");
+        const int64_t npk = q_off[n_ssm];
+        for (int i = 0; i < n_ssm; ++i) {
+            SOLO_REQUIRE(lib_row[i] < L.n, SOLO_EINVAL, "SSM %d: library row %d outside the store of charge %d (%lld rows)",
+                         i, lib_row[i], charge, (long long)L.n);
+            const int64_t len = q_off[i + 1] - q_off[i];
+            SOLO_REQUIRE(len >= 0, SOLO_EINVAL, "query offsets must be non-decreasing");
+            if (lib_row[i] < 0) continue;
+            SOLO_REQUIRE(n_pairs[i] <= max_pairs, SOLO_EINVAL, "SSM %d: %d pairs > max_pairs %d", i, n_pairs[i], max_pairs);
+            for (int k = 0; k < n_pairs[i]; ++k)
+                SOLO_REQUIRE((int64_t)pairs[((int64_t)i * max_pairs + k) * 2] < len, SOLO_EINVAL,
+                             "SSM %d: pair %d names query peak %u of %lld", i, k, pairs[((int64_t)i * max_pairs + k) * 2],
+                             (long long)len);
+        }
+        DevBuf &dmz = h->scratch[25], &din = h->scratch[26], &doff = h->scratch[27], &dpm = h->scratch[28],
+               &drow = h->scratch[29], &dpairs = h->scratch[30], &dnp = h->scratch[31];
+        h2d(h, dmz, q_mz, (size_t)npk * (q_mz_is_f64 ? 8 : 4));
+        h2d(h, din, q_intensity, (size_t)npk * 4);
+        h2d(h, doff, q_off, (size_t)(n_ssm + 1) * 8);
+        h2d(h, dpm, q_prec_mz, (size_t)n_ssm * 8);
+        h2d(h, drow, lib_row, (size_t)n_ssm * 4);
+        h2d(h, dpairs, pairs, (size_t)n_ssm * max_pairs * 8);
+        h2d(h, dnp, n_pairs, (size_t)n_ssm * 4);
+        FeatureArgs a;
+        memset(&a, 0, sizeof a);
+        a.q_mz32 = q_mz_is_f64 ? nullptr : dmz.as<float>();
+        a.q_mz64 = q_mz_is_f64 ? dmz.as<double>() : nullptr;
+        a.q_int = din.as<float>();
+        a.q_off = doff.as<int64_t>();
+        a.q_prec_mz = dpm.as<double>();
+        a.q_charge_all = charge;
+        fill_library(a, L);
+        a.lib_row = drow.as<int32_t>();
+        a.pairs = dpairs.as<uint32_t>();
+        a.n_pairs = dnp.as<int32_t>();
+        a.max_pairs = max_pairs;
+        a.n = n_ssm;
+        run_features(h, a, q_prec_charge, sequence_len, out);
+    });
+}
+
+int solo_ssm_features_staged(solo_handle *h, int charge, const int32_t *q_prec_charge, const int32_t *sequence_len,
+                             double *out) {
+    if (!h || !out) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(h->r_nq == h->nq && h->nq > 0, SOLO_ESTATE, "no search results staged in the active slot");
+        LibraryStore &L = get_lib(h, charge);
+        FeatureArgs a;
+        memset(&a, 0, sizeof a);
+        a.q_mz32 = h->q_mz.as<float>();
+        a.q_mz64 = h->q_mz_is_f64 > 0 ? h->q_mz_vec.as<double>() : nullptr;
+        a.q_int = h->q_int.as<float>();
+        a.q_off = h->q_off.as<int64_t>();
+        a.q_prec_mz = h->q_prec_mz.as<double>();
+        a.q_charge_all = charge;
+        fill_library(a, L);
+        a.lib_row = h->r_best_row.as<int32_t>();
+        a.pairs = h->r_pairs.as<uint32_t>();
+        a.n_pairs = h->r_n_pairs.as<int32_t>();
+        a.max_pairs = h->r_max_pairs;
+        a.n = h->nq;
+        run_features(h, a, q_prec_charge, sequence_len, out);
+    });
 }
 
 }  // extern "C"

@@ -278,6 +278,31 @@ struct ScoreArgs {
     int32_t *overflow;   // device counter of match-list overflows
 };
 void launch_best_match(solo_handle *h, const ScoreArgs &a);
+
+// K6 (k6_ssm_features.cu): SSM feature table, all device pointers
+struct FeatureArgs {
+    const float *q_mz32;
+    const double *q_mz64;
+    const float *q_int;
+    const int64_t *q_off;
+    const double *q_prec_mz;
+    const int32_t *q_charge;      // per SSM, or null with q_charge_all
+    int q_charge_all;
+    const float *l_mz;
+    const float *l_int;
+    const int64_t *l_off;
+    const double *l_prec_mz;
+    const int32_t *lib_row;       // library store row matched to query i (< 0: no SSM)
+    const uint32_t *pairs;        // (n, max_pairs, 2)
+    const int32_t *n_pairs;
+    int max_pairs;
+    const int32_t *sequence_len;  // may be null
+    int64_t n_peak_bins;
+    int n;
+    double *out;                  // (n, N_FEATURES)
+    int32_t *bad;                 // counter of SSMs beyond the peak capacity
+};
+void launch_ssm_features(solo_handle *h, const FeatureArgs &a);
 void k5_build_aux(solo_handle *h, LibraryStore &L);
 
 }  // namespace solo

@@ -279,6 +279,46 @@ class SoloEngine:
         self.search_staged(charge, params)
         return self.fetch_results(out)
 
+    # ------------------------------------------------------------------ K6: SSM features
+    def feature_names(self):
+        return [self._lib.solo_ssm_feature_name(i).decode() for i in range(_lib.N_SSM_FEATURES)]
+
+    def ssm_features(self, charge: int, q: dict, lib_row: np.ndarray, pairs: np.ndarray, n_pairs: np.ndarray,
+                     q_charge: Optional[np.ndarray] = None, sequence_len: Optional[np.ndarray] = None,
+                     mz_vec: Optional[np.ndarray] = None) -> np.ndarray:
+        """Feature table (n_ssm, 44) float64 for SSMs between the queries of peak store `q` and rows
+        `lib_row` of the loaded library store of `charge` (reference utils._compute_ssm_features).
+        `pairs` is (n_ssm, max_pairs, 2) as returned by the search; `mz_vec` optionally carries the
+        query m/z in float64 (the precision the caller's spectra hold)."""
+        is64 = mz_vec is not None and mz_vec.dtype == np.float64
+        qmz = _c(mz_vec if is64 else q["mz"], np.float64 if is64 else np.float32)
+        qin = _c(q["inten"], np.float32)
+        qoff = _c(q["off"], np.int64)
+        qpm = _c(q["prec_mz"], np.float64)
+        n = len(qoff) - 1
+        rows = _c(lib_row, np.int32)
+        pairs = _c(pairs, np.uint32)
+        npairs = _c(n_pairs, np.int32)
+        if pairs.ndim != 3 or pairs.shape[0] != n or pairs.shape[2] != 2 or rows.shape != (n,) or npairs.shape != (n,):
+            raise ValueError("pairs must be (n_ssm, max_pairs, 2); lib_row and n_pairs (n_ssm,)")
+        zc = None if q_charge is None else _c(q_charge, np.int32)
+        sl = None if sequence_len is None else _c(sequence_len, np.int32)
+        out = np.empty((n, _lib.N_SSM_FEATURES), np.float64)
+        self._check(self._lib.solo_ssm_features(self._h, int(charge), _ptr(qmz), int(is64), _ptr(qin), _ptr(qoff),
+                                                _ptr(qpm), _ptr(zc), n, _ptr(rows), _ptr(pairs), _ptr(npairs),
+                                                max(1, pairs.shape[1]), _ptr(sl), _ptr(out)))
+        return out
+
+    def ssm_features_staged(self, charge: int, q_charge: Optional[np.ndarray] = None,
+                            sequence_len: Optional[np.ndarray] = None) -> np.ndarray:
+        """The same for the batch and results resident in the active slot (after search_staged)."""
+        n = self._staged_nq
+        zc = None if q_charge is None else _c(q_charge, np.int32)
+        sl = None if sequence_len is None else _c(sequence_len, np.int32)
+        out = np.empty((n, _lib.N_SSM_FEATURES), np.float64)
+        self._check(self._lib.solo_ssm_features_staged(self._h, int(charge), _ptr(zc), _ptr(sl), _ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ mode B (lists sharded over GPUs)
     def ivf_set_owned_lists(self, charge: int, owned: Optional[np.ndarray]):
         """owned[l] != 0: list l is stored on this GPU (None: all lists)."""

@@ -109,9 +109,11 @@ class SpectralLibrary:
         self._ann_charges = set()
         self._ann_filenames = {}
         self._lib_ids = {}
+        self._lib_row_of = {}
         for charge, info in self._library_reader.spec_info["charge"].items():
             self._engine.load_library(charge, self._charge_store(charge))
             self._lib_ids[charge] = info["id"]
+            self._lib_row_of[charge] = {ident: i for i, ident in enumerate(np.asarray(info["id"]).tolist())}
         if config.mode == "ann":
             # No ANN index for infrequent precursor charges (reference :101-104).
             ann_charges = [z for z, info in self._library_reader.spec_info["charge"].items()
@@ -160,6 +162,12 @@ class SpectralLibrary:
             self._ann_charges.add(charge)
             if charge in self._ann_filenames:  # reference :181
                 self._engine.ivf_write_index(charge, self._ann_filenames[charge])
+
+    def compute_ssm_features(self, ssms: List[SpectrumSpectrumMatch]) -> Dict[str, List]:
+        """Reference utils._compute_ssm_features (utils.py:276-457) for SSMs of this library: one K6
+        launch per precursor charge against the device-resident peak stores."""
+        from .utils import _compute_ssm_features
+        return _compute_ssm_features(ssms, engine=self._engine, library_rows=self._lib_row_of)
 
     def shutdown(self) -> None:
         self._library_reader.close()

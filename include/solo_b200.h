@@ -195,6 +195,28 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
                       const double *q_prec_mz, int nq, int32_t *best_row, double *best_score,
                       int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand);
 
+/* ---- K6: SSM feature table for rescoring --------------------------------
+ * Replaces utils._compute_ssm_features (utils.py:276-457): for every spectrum-spectrum match the 44
+ * numeric columns that function derives from spectrum_similarity.SpectrumSimilarityCalculator(ssm) and
+ * SpectrumSimilarityCalculator(ssm, top=5) (spectrum_similarity.py:13-730), one row per SSM, float64,
+ * columns in the order of solo_ssm_feature_name(0..SOLO_N_SSM_FEATURES-1) (= the keys of the reference's
+ * `features` dict without index / sequence / is_target). The library side of each SSM is a row of the
+ * loaded peak store of `charge`; hypergeometric_score uses the vectoriser's (min_mz, max_mz, bin_size)
+ * like the reference (utils.py:398-404). SSMs with lib_row < 0 or without peak matches get NaN rows
+ * (the reference skips them, utils.py:332-333). q_prec_charge NULL: every query has charge `charge`;
+ * sequence_len NULL: column 0 is 0. pairs/n_pairs/max_pairs have the layout of solo_fetch_results. */
+#define SOLO_N_SSM_FEATURES 44
+const char *solo_ssm_feature_name(int column);
+int solo_ssm_features(solo_handle *h, int charge, const void *q_mz, int q_mz_is_f64, const float *q_intensity,
+                      const int64_t *q_off, const double *q_prec_mz, const int32_t *q_prec_charge, int n_ssm,
+                      const int32_t *lib_row, const uint32_t *pairs, const int32_t *n_pairs, int max_pairs,
+                      const int32_t *sequence_len, double *out /* n_ssm x SOLO_N_SSM_FEATURES */);
+/* The same for the batch and the results resident in the active slot after solo_search_staged /
+ * solo_search_batch: nothing but the two optional per-query int arrays goes up, only the table comes
+ * back. out is (staged queries) x SOLO_N_SSM_FEATURES. */
+int solo_ssm_features_staged(solo_handle *h, int charge, const int32_t *q_prec_charge,
+                             const int32_t *sequence_len, double *out);
+
 /* ---- mode B: inverted lists sharded over GPUs ---------------------
  * The reference has no multi-GPU path; these entry points are what a one-process-per-GPU driver
  * needs around its collective (NCCL all-gather of the per-GPU top-k rows). All pointers named d_*

@@ -34,6 +34,7 @@ def build(force: bool = False) -> None:
             os.path.getmtime(_PORT) < os.path.getmtime(os.path.join(_HERE, "solo_oracle.cpp"))):
         subprocess.check_call(["make", "-C", _HERE, "_build/libsolo_oracle.so"],
                               stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "_build/libk6_host_check.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src/ann_solo") and (force or not os.path.isfile(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
