@@ -302,6 +302,7 @@ def run_solo(args, wl, rank, world, local_rank):
 
     # the CPU baseline is reported by the single-GPU run only (torchrun also pins OMP_NUM_THREADS=1)
     cpu = cpu_baseline(wl, per_charge, q_by_charge, eng) if (not args.no_cpu_baseline and world == 1) else None
+    extras = measure_extras(eng, charges, q_by_charge, nq_rank, torch) if args.extras else None
     line = {
         "metric": "query spectra/sec, cascade open search", "value": round(value, 1), "unit": "spectra/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3),
@@ -315,7 +316,50 @@ def run_solo(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stages,
         "cpu_baseline": cpu,
     }
+    if extras:
+        line["extras"] = extras
     _emit(json.dumps(line))
+
+
+def measure_extras(eng, charges, q_by_charge, nq_rank, torch):
+    """--extras: the widened rows of SURVEY.md §8f next to the hot path, on the same resident data.
+    N4: K6 SSM feature table for the SSMs the last step produced (every charge), through the C-ABI with
+    the (n, 44) float64 table copied to the host. N2: faiss.write_index / read_index of the smallest
+    charge's index (float32 codes) to and from local disk."""
+    import tempfile
+    out = {}
+    n_ssm, reps = 0, 5
+    for z in charges:  # warm-up + count
+        eng.select_slot(z)
+        t = eng.ssm_features_staged(z)
+        n_ssm += int(np.isfinite(t[:, 11]).sum())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for z in charges:
+            eng.select_slot(z)
+            eng.ssm_features_staged(z)
+    dt = (time.perf_counter() - t0) / reps
+    out["k6_ssm_features"] = {"ssm_per_s": round(n_ssm / dt, 1), "ms_per_batch": round(dt * 1e3, 3), "ssms": n_ssm,
+                              "columns": 44, "d2h_bytes_per_batch": int(nq_rank * 44 * 8),
+                              "note": "staged batch of every charge; wall clock around the synchronous C-ABI calls"}
+    z = min(charges, key=lambda c: eng.ivf_info(c)[0])
+    ntotal, nlist, d = eng.ivf_info(z)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, f"bench_{z}.idxann")
+        t0 = time.perf_counter()
+        eng.ivf_write_index(z, path)
+        t_w = time.perf_counter() - t0
+        size = os.path.getsize(path)
+        t0 = time.perf_counter()
+        eng.ivf_read_index(9000 + z, path)
+        t_r = time.perf_counter() - t0
+        same = bool(np.array_equal(eng.ivf_assignment(9000 + z), eng.ivf_assignment(z)))
+        eng.ivf_reset(9000 + z)
+    out["idxann"] = {"charge": int(z), "vectors": int(ntotal), "nlist": int(nlist), "file_bytes": int(size),
+                     "write_s": round(t_w, 3), "write_gbs": round(size / t_w / 1e9, 3), "read_s": round(t_r, 3),
+                     "read_gbs": round(size / t_r / 1e9, 3), "assignment_identical_after_read": same}
+    return out
 
 
 def run_sharded(args, wl, rank, world, eng, charges, q_by_charge, params, torch, dist):
@@ -480,6 +524,9 @@ def main():
     ap.add_argument("--impl", default="solo", choices=["solo", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SOLO_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time the widened rows (K6 SSM feature table, .idxann write/read) on the same data; "
+                         "adds an 'extras' object to the JSON line")
     ap.add_argument("--sharded", action="store_true",
                     help="mode B: inverted lists sharded over the ranks, one global query batch, NCCL all-gather "
                          "of the per-GPU top-k rows + device merge (strong scaling); default is mode A")
