@@ -30,6 +30,15 @@ class SearchParams(C.Structure):
                 ("mz_is_f64", C.c_int32), ("max_pairs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ProcessParams(C.Structure):
+    _fields_ = [("min_mz", C.c_double), ("max_mz", C.c_double), ("min_mz_range", C.c_double),
+                ("remove_precursor_tolerance", C.c_double), ("min_intensity", C.c_double), ("min_peaks", C.c_int32),
+                ("max_peaks", C.c_int32), ("remove_precursor", C.c_int32), ("scaling", C.c_int32)]
+
+
+SCALING = {None: 0, "root": 1, "sqrt": 1, "rank": 2}
+
+
 class IdxannInfo(C.Structure):
     _fields_ = [("d", C.c_int32), ("metric", C.c_int32), ("is_trained", C.c_int32), ("reserved", C.c_int32),
                 ("ntotal", C.c_int64), ("nlist", C.c_int64), ("nprobe", C.c_int64), ("code_size", C.c_int64),
@@ -76,6 +85,10 @@ SYMBOLS = {
     "solo_fetch_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "solo_search_batch": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "solo_process_spectra": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "solo_splib_count": (C.c_int, [C.c_char_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.c_char_p, C.c_int]),
+    "solo_splib_read": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.c_char_p, C.c_int]),
     "solo_ssm_feature_name": (C.c_char_p, [C.c_int]),
     "solo_ssm_features": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp]),

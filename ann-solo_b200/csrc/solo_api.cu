@@ -78,6 +78,21 @@ static int guarded(solo_handle *h, F &&f) {
     }
 }
 
+template <typename F>
+static int guarded_nohandle(char *errbuf, int errbuf_len, F &&f) {
+    if (errbuf && errbuf_len > 0) errbuf[0] = 0;
+    try {
+        f();
+        return SOLO_OK;
+    } catch (const Error &e) {
+        if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", e.msg.c_str());
+        return e.code;
+    } catch (const std::exception &e) {
+        if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", e.what());
+        return SOLO_EINVAL;
+    }
+}
+
 static void h2d(solo_handle *h, DevBuf &b, const void *src, size_t bytes) {
     b.ensure(std::max<size_t>(bytes, 16));
     if (bytes) SOLO_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -934,6 +949,98 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
     rc = solo_search_staged(h, charge, p);
     if (rc) return rc;
     return solo_fetch_results(h, best_row, best_score, n_pairs, pairs, n_cand);
+}
+
+// ---- K0 / .splib: ingestion -----------------------------------------------------------------
+int solo_splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes, char *errbuf,
+                     int errbuf_len) {
+    if (!path || !n_spectra || !n_peaks || !n_peptide_bytes) return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len, [&] { splib_count(path, n_spectra, n_peaks, n_peptide_bytes); });
+}
+
+int solo_splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes, uint32_t *identifier,
+                    double *prec_mz, int32_t *prec_charge, uint8_t *is_decoy, int64_t *file_offset,
+                    int64_t *peak_offsets, float *mz, float *intensity, uint8_t *peak_charge, int64_t *peptide_offsets,
+                    char *peptides, char *errbuf, int errbuf_len) {
+    if (!path || !identifier || !prec_mz || !prec_charge || !is_decoy || !file_offset || !peak_offsets || !mz ||
+        !intensity || !peak_charge || !peptide_offsets || !peptides)
+        return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len, [&] {
+        splib_read(path, n_spectra, n_peaks, n_peptide_bytes, identifier, prec_mz, prec_charge, is_decoy, file_offset,
+                   peak_offsets, mz, intensity, peak_charge, peptide_offsets, peptides);
+    });
+}
+
+int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity, const int64_t *offsets,
+                         const double *prec_mz, const int32_t *prec_charge, int64_t n, const solo_process_params *p,
+                         void *out_mz, float *out_intensity, int32_t *out_index, int32_t *out_count, uint8_t *out_valid) {
+    if (!h || !p || n < 0 || (n > 0 && (!mz || !intensity || !offsets || !out_mz || !out_intensity || !out_index ||
+                                        !out_count || !out_valid)))
+        return SOLO_EINVAL;
+    return guarded(h, [&] {
+        if (n == 0) return;
+        SOLO_REQUIRE(p->max_peaks >= 1 && p->max_peaks <= 128, SOLO_ECAPACITY, "max_peaks must be in [1, 128] (got %d)",
+                     p->max_peaks);
+        SOLO_REQUIRE(p->scaling >= SOLO_SCALING_NONE && p->scaling <= SOLO_SCALING_RANK, SOLO_EINVAL,
+                     "Unknown intensity scaling");
+        SOLO_REQUIRE(!p->remove_precursor || (prec_mz && prec_charge), SOLO_EINVAL,
+                     "remove_precursor needs precursor m/z and charge");
+        SOLO_REQUIRE(n < (int64_t)0x7fffffff && offsets[0] == 0, SOLO_EINVAL, "bad offsets");
+        const int64_t npk = offsets[n];
+        const size_t esz = mz_is_f64 ? 8 : 4;
+        for (int64_t i = 0; i < n; ++i) {
+            SOLO_REQUIRE(offsets[i + 1] >= offsets[i], SOLO_EINVAL, "offsets must be non-decreasing");
+            SOLO_REQUIRE(offsets[i + 1] - offsets[i] <= 8192, SOLO_ECAPACITY,
+                         "spectrum %lld holds %lld raw peaks; the kernel stages at most 8192", (long long)i,
+                         (long long)(offsets[i + 1] - offsets[i]));
+        }
+        DevBuf &dmz = h->scratch[21], &din = h->scratch[22], &doff = h->scratch[23], &dpm = h->scratch[24],
+               &dz = h->scratch[25], &omz = h->scratch[26], &oin = h->scratch[27], &oidx = h->scratch[28],
+               &ocnt = h->scratch[29], &oval = h->scratch[30], &err = h->scratch[31];
+        h2d(h, dmz, mz, (size_t)npk * esz);
+        h2d(h, din, intensity, (size_t)npk * 4);
+        h2d(h, doff, offsets, (size_t)(n + 1) * 8);
+        if (prec_mz) h2d(h, dpm, prec_mz, (size_t)n * 8);
+        if (prec_charge) h2d(h, dz, prec_charge, (size_t)n * 4);
+        const size_t rows = (size_t)n * p->max_peaks;
+        omz.ensure(rows * esz);
+        oin.ensure(rows * 4);
+        oidx.ensure(rows * 4);
+        ocnt.ensure((size_t)n * 4);
+        oval.ensure((size_t)n);
+        err.ensure(4);
+        SOLO_CUDA(cudaMemsetAsync(err.p, 0, 4, h->stream));
+        SOLO_CUDA(cudaMemsetAsync(omz.p, 0, rows * esz, h->stream));
+        SOLO_CUDA(cudaMemsetAsync(oin.p, 0, rows * 4, h->stream));
+        SOLO_CUDA(cudaMemsetAsync(oidx.p, 0xff, rows * 4, h->stream));
+        ProcessArgs a;
+        a.mz = dmz.p;
+        a.inten = din.as<float>();
+        a.off = doff.as<int64_t>();
+        a.prec_mz = prec_mz ? dpm.as<double>() : nullptr;
+        a.prec_charge = prec_charge ? dz.as<int32_t>() : nullptr;
+        a.n = (int)n;
+        a.p = *p;
+        a.out_mz = omz.p;
+        a.out_int = oin.as<float>();
+        a.out_idx = oidx.as<int32_t>();
+        a.out_cnt = ocnt.as<int32_t>();
+        a.out_valid = oval.as<uint8_t>();
+        a.err = err.as<int32_t>();
+        launch_process(h, a, mz_is_f64);
+        int32_t n_err = 0;
+        auto d2h = [&](void *dst, const DevBuf &src, size_t bytes) {
+            SOLO_CUDA(cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+        };
+        d2h(out_mz, omz, rows * esz);
+        d2h(out_intensity, oin, rows * 4);
+        d2h(out_index, oidx, rows * 4);
+        d2h(out_count, ocnt, (size_t)n * 4);
+        d2h(out_valid, oval, (size_t)n);
+        d2h(&n_err, err, 4);
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        SOLO_REQUIRE(n_err == 0, SOLO_ECAPACITY, "%d spectra exceeded the raw-peak capacity", n_err);
+    });
 }
 
 // ---- K6: SSM feature table ----------------------------------------------------------------

@@ -303,6 +303,30 @@ struct FeatureArgs {
     int32_t *bad;                 // counter of SSMs beyond the peak capacity
 };
 void launch_ssm_features(solo_handle *h, const FeatureArgs &a);
+
+// K0 (k0_process.cu): batched process_spectrum
+struct ProcessArgs {
+    const void *mz;          // float32 or float64, ascending inside every spectrum
+    const float *inten;
+    const int64_t *off;
+    const double *prec_mz;
+    const int32_t *prec_charge;
+    int n;
+    solo_process_params p;
+    // outputs, row stride = p.max_peaks
+    void *out_mz;            // same type as mz
+    float *out_int;
+    int32_t *out_idx;        // index of the kept peak inside its raw spectrum
+    int32_t *out_cnt;        // peaks kept (0 for invalid spectra)
+    uint8_t *out_valid;
+    int32_t *err;            // [0]: spectra with more than K0_MAX_RAW peaks
+};
+void launch_process(solo_handle *h, const ProcessArgs &a, int mz_is_f64);
+// splib_io.cu: SpectraST .splib -> CSR arrays (host only)
+void splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes);
+void splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes, uint32_t *id,
+                double *prec_mz, int32_t *prec_charge, uint8_t *is_decoy, int64_t *file_offset, int64_t *peak_off,
+                float *mz, float *inten, uint8_t *peak_charge, int64_t *pep_off, char *pep);
 void k5_build_aux(solo_handle *h, LibraryStore &L);
 
 }  // namespace solo

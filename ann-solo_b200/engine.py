@@ -279,6 +279,52 @@ class SoloEngine:
         self.search_staged(charge, params)
         return self.fetch_results(out)
 
+    # ------------------------------------------------------------------ K0: process_spectrum, batched
+    def process_spectra(self, store: dict, min_mz=11.0, max_mz=2010.0, min_peaks=10, min_mz_range=250.0,
+                        remove_precursor=False, remove_precursor_tolerance=0.0, min_intensity=0.01, max_peaks=50,
+                        scaling="rank", resolution=None, mz_vec: Optional[np.ndarray] = None) -> dict:
+        """Reference spectrum.process_spectrum (spectrum.py:57-119) for every spectrum of a raw peak
+        store in one launch. Returns a processed peak store (``valid`` = is_valid; invalid spectra
+        keep no peaks) plus ``src`` = index of every kept peak inside its raw spectrum; peak charges
+        (``chg``) and float64 m/z follow the kept peaks."""
+        if resolution is not None:
+            raise ValueError("resolution (round + merge) is not implemented on the device")
+        if scaling not in _lib.SCALING:
+            raise ValueError("Unknown intensity scaling")
+        is64 = mz_vec is not None and mz_vec.dtype == np.float64
+        mz = _c(mz_vec if is64 else store["mz"], np.float64 if is64 else np.float32)
+        inten = _c(store["inten"], np.float32)
+        off = _c(store["off"], np.int64)
+        n = len(off) - 1
+        pm = _c(store["prec_mz"], np.float64) if store.get("prec_mz") is not None else None
+        pz = _c(store["prec_z"], np.int32) if store.get("prec_z") is not None else None
+        prm = _lib.ProcessParams(float(min_mz), float(max_mz), float(min_mz_range), float(remove_precursor_tolerance),
+                                 float(min_intensity), int(min_peaks), int(max_peaks), int(bool(remove_precursor)),
+                                 _lib.SCALING[scaling])
+        o_mz = np.empty((n, max_peaks), mz.dtype)
+        o_in = np.empty((n, max_peaks), np.float32)
+        o_ix = np.empty((n, max_peaks), np.int32)
+        o_ct = np.empty(n, np.int32)
+        o_va = np.empty(n, np.uint8)
+        self._check(self._lib.solo_process_spectra(self._h, _ptr(mz), int(is64), _ptr(inten), _ptr(off), _ptr(pm),
+                                                   _ptr(pz), n, C.byref(prm), _ptr(o_mz), _ptr(o_in), _ptr(o_ix),
+                                                   _ptr(o_ct), _ptr(o_va)))
+        keep = np.arange(max_peaks)[None, :] < o_ct[:, None]
+        new_off = np.zeros(n + 1, np.int64)
+        np.cumsum(o_ct, out=new_off[1:])
+        src = o_ix[keep]
+        gsrc = np.repeat(off[:-1], o_ct) + src
+        out = dict(mz=o_mz[keep].astype(np.float32), inten=o_in[keep], off=new_off, valid=o_va, src=src,
+                   prec_mz=store.get("prec_mz"), prec_z=store.get("prec_z"))
+        if is64:
+            out["mz64"] = o_mz[keep]
+        if store.get("chg") is not None:
+            out["chg"] = np.asarray(store["chg"], np.uint8)[gsrc]
+        for key in ("is_decoy", "id", "peptide", "file_offset"):
+            if key in store:
+                out[key] = store[key]
+        return out
+
     # ------------------------------------------------------------------ K6: SSM features
     def feature_names(self):
         return [self._lib.solo_ssm_feature_name(i).decode() for i in range(_lib.N_SSM_FEATURES)]

@@ -195,6 +195,43 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
                       const double *q_prec_mz, int nq, int32_t *best_row, double *best_score,
                       int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand);
 
+/* ---- library ingestion and preprocessing -----------------------------------
+ * K0 replaces spectrum.process_spectrum (spectrum.py:57-119) per spectrum by one launch over a CSR
+ * batch of raw spectra (m/z ascending): set_mz_range, validity (:14-36, re-checked after every step),
+ * remove_precursor_peak(tol, 'Da', 2), filter_intensity(min_intensity, max_peaks),
+ * scale_intensity('root' | 'rank', max_rank = max_peaks), L2 norm. The config keys are the reference's
+ * (config.py:71-117); `resolution` must be None (not implemented on the device). Outputs are
+ * fixed-stride rows of max_peaks entries: out_mz (same type as mz), out_intensity, out_index (position
+ * of the kept peak in its raw spectrum — carries annotations/peak charges along), out_count (0 for an
+ * invalid spectrum), out_valid (is_valid). */
+enum { SOLO_SCALING_NONE = 0, SOLO_SCALING_ROOT = 1, SOLO_SCALING_RANK = 2 };
+typedef struct solo_process_params {
+    double min_mz, max_mz;                 /* config.min_mz / max_mz */
+    double min_mz_range;                   /* config.min_mz_range */
+    double remove_precursor_tolerance;     /* config.remove_precursor_tolerance (Da) */
+    double min_intensity;                  /* config.min_intensity */
+    int32_t min_peaks;                     /* config.min_peaks */
+    int32_t max_peaks;                     /* config.max_peaks_used(_library), <= 128 */
+    int32_t remove_precursor;              /* config.remove_precursor */
+    int32_t scaling;                       /* config.scaling: SOLO_SCALING_* ('sqrt' == root) */
+} solo_process_params;
+int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity,
+                         const int64_t *offsets, const double *prec_mz, const int32_t *prec_charge, int64_t n,
+                         const solo_process_params *p, void *out_mz, float *out_intensity, int32_t *out_index,
+                         int32_t *out_count, uint8_t *out_valid);
+/* SpectraST binary libraries: replaces parsers.SplibParser (parsers.pyx:41-186) for bulk ingestion.
+ * Host code, no handle: count, let the caller allocate, fill. Spectra come in file order; peptide
+ * strings are concatenated (peptide_offsets[n+1]); peak_charge is what the reference's annotation
+ * parser yields for a/b/y ions and 0 elsewhere; file_offset is the byte offset the reference stores
+ * in spec_info['offset'] (reader.py:180-187). errbuf receives the message on failure. */
+int solo_splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes,
+                     char *errbuf, int errbuf_len);
+int solo_splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes,
+                    uint32_t *identifier, double *prec_mz, int32_t *prec_charge, uint8_t *is_decoy,
+                    int64_t *file_offset, int64_t *peak_offsets, float *mz, float *intensity,
+                    uint8_t *peak_charge, int64_t *peptide_offsets, char *peptides, char *errbuf,
+                    int errbuf_len);
+
 /* ---- K6: SSM feature table for rescoring --------------------------------
  * Replaces utils._compute_ssm_features (utils.py:276-457): for every spectrum-spectrum match the 44
  * numeric columns that function derives from spectrum_similarity.SpectrumSimilarityCalculator(ssm) and

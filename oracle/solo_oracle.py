@@ -283,9 +283,12 @@ def process_spectrum_np(mz, intensity, precursor_mz, precursor_charge, *, min_mz
     idx = np.arange(len(mz))
 
     def valid(m):
-        return len(m) >= min_peaks and (m[-1] - m[0]) >= min_mz_range
+        return len(m) >= min_peaks and len(m) > 0 and (m[-1] - m[0]) >= m.dtype.type(min_mz_range)
 
-    keep = (mz >= min_mz) & (mz <= max_mz)  # set_mz_range
+    # scalars enter comparisons in the precision of the m/z array (what NumPy >= 2 does for Python
+    # floats; spelled out so that the result does not depend on the NumPy version or scalar types)
+    T = mz.dtype.type
+    keep = (mz >= T(min_mz)) & (mz <= T(max_mz))  # set_mz_range
     mz, intensity, idx = mz[keep], intensity[keep], idx[keep]
     if not valid(mz):
         return mz, intensity, False, idx
@@ -301,17 +304,17 @@ def process_spectrum_np(mz, intensity, precursor_mz, precursor_charge, *, min_mz
         if not valid(mz):
             return mz, intensity, False, idx
     if remove_precursor:  # remove_precursor_peak(tol, 'Da', isotope=2)
-        neutral = (precursor_mz - 1.0072766) * precursor_charge
+        neutral = (float(precursor_mz) - 1.0072766) * int(precursor_charge)
         rm = np.zeros(len(mz), bool)
-        for c in range(precursor_charge, 0, -1):
+        for c in range(int(precursor_charge), 0, -1):
             for iso in range(3):
-                rm |= np.abs(mz - ((neutral + iso) / c + 1.0072766)) <= remove_precursor_tolerance
+                rm |= np.abs(mz - T((neutral + iso) / c + 1.0072766)) <= T(remove_precursor_tolerance)
         mz, intensity, idx = mz[~rm], intensity[~rm], idx[~rm]
         if not valid(mz):
             return mz, intensity, False, idx
     # filter_intensity(min_intensity, max_num_peaks)
     order = np.argsort(intensity, kind="stable")
-    thr = min_intensity * (intensity[order[-1]] if len(order) else 0.0)
+    thr = np.float32(min_intensity) * (intensity[order[-1]] if len(order) else np.float32(0.0))
     start = 0
     while start < len(order) and intensity[order[start]] <= thr:
         start += 1

@@ -1,0 +1,81 @@
+"""``.splib`` ingestion on the host (no GPU): the native parser behind solo_splib_count / solo_splib_read
+against the oracle's pure-Python restatement of reference parsers.pyx:41-186 on synthetic files."""
+import numpy as np
+import pytest
+
+from oracle import splib_io
+
+ANNOTATIONS = ["b2/0.01", "y3^2/0.02", "y10-18/0.1", "a4/0.0,b4-28/0.1", "?", "p^2/0.3", "y7^3i/0.0", "b12^2-17/0.2",
+               "IWA/0.1", "y1/-0.01", "b/0.1", "y15^12/0.0", ""]
+
+
+def _library(n=60, seed=1):
+    rng = np.random.default_rng(seed)
+    specs = []
+    for i in range(n):
+        k = int(rng.integers(0, 40))
+        specs.append(dict(id=1000 + 7 * i, peptide="PEPT" + "KR"[i % 2] * (i % 6 + 1), charge=int(rng.integers(1, 6)),
+                          prec_mz=float(rng.uniform(300, 1200)), mz=np.sort(rng.uniform(100, 1900, k)),
+                          intensity=rng.uniform(1, 1e4, k),
+                          annotations=[ANNOTATIONS[int(j)] for j in rng.integers(0, len(ANNOTATIONS), k)],
+                          decoy=i % 3 == 0, mods="|1|3,C,Carbamidomethyl" if i % 2 else ""))
+    return specs
+
+
+def test_annotation_charges_follow_the_reference_parser():
+    # parsers.pyx:160-186: a/b/y ions only; '<type><index>/' -> 1; '^z' -> z; everything else unannotated
+    want = dict(zip(ANNOTATIONS, [1, 2, 0, 1, 0, 0, 3, 2, 0, 1, 0, 12, 0]))
+    for a, c in want.items():
+        assert splib_io.parse_annotation(a.encode()) == c, a
+
+
+def test_native_parser_equals_oracle_reader(tmp_path):
+    from ann_solo_b200 import parsers
+    specs = _library()
+    p = str(tmp_path / "lib.splib")
+    offsets = splib_io.write_splib(p, specs)
+    want, got = splib_io.read_splib(p), parsers.read_splib(p)
+    for k in ("id", "prec_z", "prec_mz", "is_decoy", "file_offset", "off", "mz", "inten", "chg"):
+        assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), k
+    assert got["peptide"] == want["peptide"] == [s["peptide"] for s in specs]
+    assert list(got["file_offset"]) == offsets
+    assert np.array_equal(got["mz"], np.concatenate([s["mz"] for s in specs]).astype(np.float32))
+    assert got["is_decoy"].tolist() == [int(s["decoy"]) for s in specs]
+
+
+def test_splib_parser_object_surface(tmp_path):
+    """SplibParser.read_spectrum keeps the reference's (spectrum, offset) / StopIteration contract."""
+    from ann_solo_b200.parsers import SplibParser
+    specs = _library(12, seed=3)
+    p = str(tmp_path / "lib.splib")
+    offsets = splib_io.write_splib(p, specs)
+    parser = SplibParser(p.encode())
+    parser.seek_first_spectrum()
+    seen = []
+    while True:
+        try:
+            spectrum, off = parser.read_spectrum()
+        except StopIteration:
+            break
+        seen.append(off)
+        s = specs[len(seen) - 1]
+        assert spectrum.identifier == str(s["id"]) and spectrum.peptide == s["peptide"]
+        assert spectrum.precursor_charge == s["charge"] and spectrum.precursor_mz == s["prec_mz"]
+        assert spectrum.is_decoy == s["decoy"] and spectrum.mz.dtype == np.float32
+        chg = [0 if a is None else a.charge for a in spectrum.annotation]
+        assert chg == [splib_io.parse_annotation(a.encode()) for a in s["annotations"]]
+    assert seen == offsets
+    spectrum, off = parser.read_spectrum(offsets[5])
+    assert off == offsets[5] and spectrum.identifier == str(specs[5]["id"])
+
+
+def test_errors(tmp_path):
+    from ann_solo_b200 import parsers
+    with pytest.raises(FileNotFoundError):
+        parsers.read_splib(str(tmp_path / "missing.splib"))
+    p = str(tmp_path / "lib.splib")
+    offsets = splib_io.write_splib(p, _library(5, seed=4))
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:offsets[-1] + 9])   # inside the last spectrum's name line: no precursor m/z follows
+    with pytest.raises(ValueError, match="truncated|claims|malformed"):
+        parsers.read_splib(p)
