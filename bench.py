@@ -343,6 +343,23 @@ def measure_extras(eng, charges, q_by_charge, nq_rank, torch):
     out["k6_ssm_features"] = {"ssm_per_s": round(n_ssm / dt, 1), "ms_per_batch": round(dt * 1e3, 3), "ssms": n_ssm,
                               "columns": 44, "d2h_bytes_per_batch": int(nq_rank * 44 * 8),
                               "note": "staged batch of every charge; wall clock around the synchronous C-ABI calls"}
+    # N3: K0 process_spectrum over a batch of raw spectra (16,384 x ~300 peaks, gamma intensities), host buffers
+    rng = np.random.default_rng(7)
+    counts = rng.integers(100, 500, 16384)
+    roff = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=roff[1:])
+    rmz = rng.uniform(50.0, 2000.0, roff[-1]).astype(np.float32)
+    rmz = rmz[np.lexsort((rmz, np.repeat(np.arange(len(counts)), counts)))]   # ascending inside every spectrum
+    raw = dict(mz=rmz, inten=rng.gamma(0.6, 1000.0, roff[-1]).astype(np.float32), off=roff,
+               prec_mz=rng.uniform(300, 1000, len(counts)), prec_z=rng.integers(2, 5, len(counts)).astype(np.int32))
+    eng.process_spectra(raw)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        done = eng.process_spectra(raw)
+    dt = (time.perf_counter() - t0) / reps
+    out["k0_process_spectrum"] = {"spectra_per_s": round(len(counts) / dt, 1), "ms_per_batch": round(dt * 1e3, 3),
+                                  "raw_peaks": int(roff[-1]), "valid": int(done["valid"].sum()),
+                                  "note": "16,384 raw spectra, host buffers in and out, incl. the NumPy compaction"}
     z = min(charges, key=lambda c: eng.ivf_info(c)[0])
     ntotal, nlist, d = eng.ivf_info(z)
     with tempfile.TemporaryDirectory() as tmp:
