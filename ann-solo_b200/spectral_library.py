@@ -100,8 +100,18 @@ class SpectralLibrary:
         """``ann_basename``: what the reference derives from the library file name
         (``os.path.splitext(filename)[0]``, :99-100); when given, the index of every charge is read
         from / written to ``{ann_basename}_{hash[:7]}_{charge}.idxann`` like the reference does."""
-        self._library_reader = library
         self._engine = engine or SoloEngine(device)
+        if isinstance(library, (str, os.PathLike)):   # the reference's signature: SpectralLibrary(filename), :46-71
+            from .reader import SpectralLibraryReader
+            filename = os.fspath(library)
+            try:
+                library = SpectralLibraryReader(filename, self._get_hyperparameter_hash(), engine=self._engine)
+            except FileNotFoundError as e:
+                logging.error(e)
+                raise
+            if ann_basename is None:
+                ann_basename = os.path.splitext(filename)[0]
+        self._library_reader = library
         self._score_ssms = score_ssms
         self._num_probe = config.num_probe
         self._num_candidates = config.num_candidates
