@@ -37,6 +37,8 @@ k6_ssm_features_kernel(const FeatureArgs a) {
     in.q_charge = a.q_charge ? a.q_charge[i] : a.q_charge_all;
     in.sequence_len = a.sequence_len ? a.sequence_len[i] : 0;
     in.n_peak_bins = a.n_peak_bins;
+    in.lfact = a.lfact;
+    in.lbig = a.lbig;
     if (in.nq > k6::MAX_PEAKS || in.nl > k6::MAX_PEAKS || np > k6::MAX_PEAKS || np > a.max_pairs) {
         atomicAdd(a.bad, 1);
         return;

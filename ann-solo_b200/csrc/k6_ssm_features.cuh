@@ -49,27 +49,40 @@ struct SsmIn {
     double q_prec_mz, l_prec_mz;
     int q_charge, sequence_len;
     int64_t n_peak_bins;    // get_dim(min_mz, max_mz, bin_size)[0] (spectrum_similarity.py:297)
+    // log-gamma tables for the binomials of hypergeometric_score (fill_log_tables):
+    const double *lfact;    // [MAX_PEAKS + 1]      lfact[k] = lgamma(k + 1)
+    const double *lbig;     // [2 * MAX_PEAKS + 1]  lbig[k]  = lgamma(n_peak_bins + 1 - k)
 };
+
+constexpr int LFACT_LEN = MAX_PEAKS + 1, LBIG_LEN = 2 * MAX_PEAKS + 1;
+
+// host side: the two tables for a given number of m/z bins
+inline void fill_log_tables(int64_t bins, double *lfact, double *lbig) {
+    for (int k = 0; k < LFACT_LEN; ++k) lfact[k] = lgamma((double)k + 1.0);
+    for (int k = 0; k < LBIG_LEN; ++k) lbig[k] = bins + 1 - k > 0 ? lgamma((double)(bins + 1 - k)) : HUGE_VAL;
+}
 
 struct Scratch {  // per thread
     uint8_t qflag[MAX_PEAKS];  // bit 0: matched
     uint8_t lflag[MAX_PEAKS];  // bit 0: matched, bit 1: among the TOP most intense library peaks
     double x[MAX_PEAKS], y[MAX_PEAKS], rx[2 * MAX_PEAKS], ry[MAX_PEAKS];  // rx also holds the merged spectrum
     double dp[KENDALL_DP];
+    double lv[2 * MAX_PEAKS];  // per-element logs of the spectrum whose entropy is being taken
 };
 
 K6_HD double k6_inf() { return HUGE_VAL; }
 K6_HD double k6_nan() { return HUGE_VAL - HUGE_VAL; }
 
-K6_HD double log_comb(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
-
-// spectrum_similarity.py:251-309: -log P(more than `m` of the `L` library peaks match by chance)
-K6_HD double hypergeometric_score(int m, int L, int64_t bins) {
+// spectrum_similarity.py:251-309: -log P(more than `m` of the `L` library peaks match by chance);
+// comb(n, k) through the log-gamma tables: comb(L, i), comb(bins - L, L - i), comb(bins, L)
+K6_HD double hypergeometric_score(int m, int L, int64_t bins, const double *lfact, const double *lbig) {
     double p = 0.0;
-    const double ld = log_comb((double)bins, (double)L);
+    const double ld = lbig[0] - lfact[L] - lbig[L];
     for (int i = m + 1; i <= L; ++i) {
         if ((int64_t)(L - i) > bins - L) continue;  // comb() == 0
-        p += exp(log_comb((double)L, (double)i) + log_comb((double)(bins - L), (double)(L - i)) - ld);
+        const double a = lfact[L] - lfact[i] - lfact[L - i];
+        const double b = lbig[L] - lfact[L - i] - lbig[2 * L - i];
+        p += exp(a + b - ld);
     }
     if (!(p > 0.0)) return 100.0;  // guard against infinity for identical spectra (:308)
     const double s = -log(p);
@@ -178,29 +191,33 @@ K6_HD void average_ranks(const double *v, int n, double *r) {
     }
 }
 
-// scipy.stats.entropy of non-negative weights given their sum
-K6_HD double entropy_of(const double *v, int n, double sum) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) {
-        const double p = v[i] / sum;
-        if (p > 0.0) s -= p * log(p);
-    }
-    return s;
-}
-
-// spectrum_similarity.py:703-730 (_spectrum_entropy); `v` is overwritten when the weighted form applies
-K6_HD double spectrum_entropy(double *v, int n, bool weighted) {
+// spectrum_similarity.py:703-730 (_spectrum_entropy) for both variants at once: scipy.stats.entropy of
+// v (unweighted) and, when that is <= 3, of v ** (0.25 + 0.25 * entropy) (weighted; above 3 the two
+// coincide). log v is taken once per element (lv) and reused: v ** w = exp(w * lv).
+K6_HD void spectrum_entropies(const double *v, int n, double *lv, double &unweighted, double &weighted) {
     double sum = 0.0;
     for (int i = 0; i < n; ++i) sum += v[i];
-    const double s = entropy_of(v, n, sum);
-    if (!weighted || s > 3.0) return s;
+    const double lsum = log(sum);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        lv[i] = v[i] > 0.0 ? log(v[i]) : 0.0;
+        if (v[i] > 0.0) s -= (v[i] / sum) * (lv[i] - lsum);
+    }
+    unweighted = s;
+    weighted = s;
+    if (s > 3.0) return;
     const double w = 0.25 + 0.25 * s;
     double wsum = 0.0;
-    for (int i = 0; i < n; ++i) {
-        v[i] = v[i] > 0.0 ? pow(v[i], w) : 0.0;
-        wsum += v[i];
-    }
-    return entropy_of(v, n, wsum);
+    for (int i = 0; i < n; ++i)
+        if (v[i] > 0.0) wsum += exp(w * lv[i]);
+    const double lwsum = log(wsum);
+    double sw = 0.0;
+    for (int i = 0; i < n; ++i)
+        if (v[i] > 0.0) {
+            const double lp = w * lv[i] - lwsum;
+            sw -= exp(lp) * lp;
+        }
+    weighted = sw;
 }
 
 K6_HD double contrast_angle(double cosine) {  // spectrum_similarity.py:233-249
@@ -311,7 +328,7 @@ K6_HD void ssm_features(const SsmIn &in, Scratch &S, double *out) {
     out[C_MSE_MZ] = mz_sq / m;
     out[C_MSE_INT] = sq_diff / m;
     out[C_CONTRAST] = contrast_angle(dot);
-    out[C_HYPERGEOMETRIC] = hypergeometric_score(np, nl, in.n_peak_bins);
+    out[C_HYPERGEOMETRIC] = hypergeometric_score(np, nl, in.n_peak_bins, in.lfact, in.lbig);
     {
         const double p = kendalltau_pvalue(S.x, S.y, np, S.dp);
         out[C_KENDALLTAU] = p == p ? -log(p) : 0.0;        // :334-338
@@ -345,7 +362,7 @@ K6_HD void ssm_features(const SsmIn &in, Scratch &S, double *out) {
     out[C_SPEARMANR] = pearson(S.rx, S.ry, n);
 
     // ---- spectral entropy (:659-700): merged = [(mq + ml) / 2, uq / 2, ul / 2]
-    for (int w = 0; w < 2; ++w) {
+    {
         int k = 0;
         for (int j = 0; j < np; ++j)
             S.rx[k++] = ((double)in.q_int[in.pairs[2 * j]] + (double)in.l_int[in.pairs[2 * j + 1]]) * 0.5;
@@ -353,12 +370,14 @@ K6_HD void ssm_features(const SsmIn &in, Scratch &S, double *out) {
             if (!(S.qflag[i] & 1)) S.rx[k++] = (double)in.q_int[i] * 0.5;
         for (int i = 0; i < nl; ++i)
             if (!(S.lflag[i] & 1)) S.rx[k++] = (double)in.l_int[i] * 0.5;
-        const double e_merged = spectrum_entropy(S.rx, k, w == 1);
+        double mu, mw, qu, qw, lu, lw;
+        spectrum_entropies(S.rx, k, S.lv, mu, mw);
         for (int i = 0; i < nq; ++i) S.ry[i] = (double)in.q_int[i];
-        const double e_query = spectrum_entropy(S.ry, nq, w == 1);
+        spectrum_entropies(S.ry, nq, S.lv, qu, qw);
         for (int i = 0; i < nl; ++i) S.ry[i] = (double)in.l_int[i];
-        const double e_lib = spectrum_entropy(S.ry, nl, w == 1);
-        out[w ? C_ENTROPY_WEIGHTED : C_ENTROPY_UNWEIGHTED] = 1.0 - (2.0 * e_merged - e_query - e_lib) / 1.3862943611198906;
+        spectrum_entropies(S.ry, nl, S.lv, lu, lw);
+        out[C_ENTROPY_UNWEIGHTED] = 1.0 - (2.0 * mu - qu - lu) / 1.3862943611198906;
+        out[C_ENTROPY_WEIGHTED] = 1.0 - (2.0 * mw - qw - lw) / 1.3862943611198906;
     }
 
     // ---- restricted to the TOP most intense library peaks (:50-75)

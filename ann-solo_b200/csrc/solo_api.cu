@@ -1079,6 +1079,15 @@ static void run_features(solo_handle *h, FeatureArgs &a, const int32_t *h_q_char
         a.sequence_len = sl.as<int32_t>();
     }
     a.n_peak_bins = h->n_bins;   // get_dim(config.min_mz, config.max_mz, config.bin_size) (utils.py:398-404)
+    {   // log-gamma tables for the binomials of hypergeometric_score
+        std::vector<double> tab(k6::LFACT_LEN + k6::LBIG_LEN);
+        k6::fill_log_tables(h->n_bins, tab.data(), tab.data() + k6::LFACT_LEN);
+        DevBuf &dt = h->scratch[18];
+        h2d(h, dt, tab.data(), tab.size() * sizeof(double));
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));  // `tab` is pageable and dies with this scope
+        a.lfact = dt.as<double>();
+        a.lbig = dt.as<double>() + k6::LFACT_LEN;
+    }
     a.out = out.as<double>();
     a.bad = bad.as<int32_t>();
     launch_ssm_features(h, a);

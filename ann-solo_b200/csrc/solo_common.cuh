@@ -298,6 +298,7 @@ struct FeatureArgs {
     int max_pairs;
     const int32_t *sequence_len;  // may be null
     int64_t n_peak_bins;
+    const double *lfact, *lbig;   // log-gamma tables (k6::fill_log_tables)
     int n;
     double *out;                  // (n, N_FEATURES)
     int32_t *bad;                 // counter of SSMs beyond the peak capacity
