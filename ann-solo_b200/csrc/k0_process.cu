@@ -148,21 +148,21 @@ k0_process_kernel(const ProcessArgs a) {
         __syncthreads();
     }
     // rank under (intensity, index): number of kept peaks that are greater; keep the max_peaks greatest.
-    // s_keep: 1 = candidate, then 2 + rank is not needed later, so ranks go to a register pass below
-    // (two passes: first mark survivors, then rank among survivors = the same count).
+    // Survivors are exactly the peaks with fewer than max_peaks greater ones, and every peak greater than a
+    // survivor survives too, so a survivor's count is also its rank among the survivors: it is parked in
+    // the flag byte (1 + rank <= 128) for the scaling step. Flags only move between non-zero values during
+    // the pass (255 = dropped, cleared after the barrier), so concurrent readers still see "candidate".
     for (int i = tid; i < n; i += K0_THREADS) {
         if (!s_keep[i]) continue;
         const float v = s_int[i];
         int greater = 0;
         for (int j = 0; j < n; ++j)
             greater += (s_keep[j] != 0) && (s_int[j] > v || (s_int[j] == v && j > i));
-        // survivors are exactly the peaks with fewer than max_peaks greater ones; dropping the others
-        // does not change any survivor's count, so the flag can be rewritten after the barrier
-        if (greater >= P.max_peaks) s_keep[i] = 3;  // dropped (still counted by the other threads in this pass)
+        s_keep[i] = greater >= P.max_peaks ? 255 : (uint8_t)(1 + greater);
     }
     __syncthreads();
     for (int i = tid; i < n; i += K0_THREADS)
-        if (s_keep[i] == 3) s_keep[i] = 0;
+        if (s_keep[i] == 255) s_keep[i] = 0;
     __syncthreads();
     if (!valid_now()) return;
     const int kept = s_count;   // <= max_peaks
@@ -183,11 +183,7 @@ k0_process_kernel(const ProcessArgs a) {
         if (k) {
             float v = s_int[i];
             if (P.scaling == SOLO_SCALING_ROOT) v = __fsqrt_rn(v);
-            else if (P.scaling == SOLO_SCALING_RANK) {
-                int greater = 0;
-                for (int j = 0; j < n; ++j) greater += s_keep[j] && (s_int[j] > s_int[i] || (s_int[j] == s_int[i] && j > i));
-                v = (float)(P.max_peaks - greater);
-            }
+            else if (P.scaling == SOLO_SCALING_RANK) v = (float)(P.max_peaks - ((int)s_keep[i] - 1));
             o_mz[pos] = mz[i];
             o_int[pos] = v;
             o_idx[pos] = i;
