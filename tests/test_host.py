@@ -150,3 +150,20 @@ def test_merge_topk_equals_global(oracle, synth):
         Ip.append(i)
     Dm, Im = parallel.merge_topk(Dp, Ip, 40)
     assert np.array_equal(Im, I) and np.array_equal(Dm, D)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/solo_b200.h must compile as C (no C++-isms, no torch types)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "solo_b200.h"\n'
+                   'int main(void) { solo_process_params p; solo_idxann_info i; solo_search_params s;\n'
+                   '  (void)p; (void)i; (void)s; return SOLO_N_SSM_FEATURES == 44 ? 0 : 1; }\n')
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "hdr.o")])
+    header = open(os.path.join(ROOT, "include", "solo_b200.h")).read()
+    assert "torch" not in header and "std::" not in header
