@@ -39,7 +39,10 @@ k6_ssm_features_kernel(const FeatureArgs a) {
     in.n_peak_bins = a.n_peak_bins;
     in.lfact = a.lfact;
     in.lbig = a.lbig;
-    if (in.nq > k6::MAX_PEAKS || in.nl > k6::MAX_PEAKS || np > k6::MAX_PEAKS || np > a.max_pairs) {
+    bool ok = in.nq <= k6::MAX_PEAKS && in.nl <= k6::MAX_PEAKS && np <= k6::MAX_PEAKS && np <= a.max_pairs;
+    for (int k = 0; ok && k < np; ++k)  // a pair naming a peak outside either spectrum is refused, never read
+        ok = in.pairs[2 * k] < (uint32_t)in.nq && in.pairs[2 * k + 1] < (uint32_t)in.nl;
+    if (!ok) {
         atomicAdd(a.bad, 1);
         return;
     }

@@ -1096,7 +1096,8 @@ static void run_features(solo_handle *h, FeatureArgs &a, const int32_t *h_q_char
     SOLO_CUDA(cudaMemcpyAsync(h_out, out.p, (size_t)n * k6::N_FEATURES * sizeof(double), cudaMemcpyDeviceToHost,
                               h->stream));
     SOLO_CUDA(cudaStreamSynchronize(h->stream));
-    SOLO_REQUIRE(n_bad == 0, SOLO_ECAPACITY, "%d SSMs hold more than %d peaks or pairs beyond max_pairs", n_bad,
+    SOLO_REQUIRE(n_bad == 0, SOLO_ECAPACITY,
+                 "%d SSMs hold more than %d peaks, more pairs than max_pairs, or a pair outside its spectra", n_bad,
                  k6::MAX_PEAKS);
 }
 

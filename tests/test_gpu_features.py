@@ -68,6 +68,11 @@ def test_skipped_rows_and_argument_checks(engine):
     bad[0, 0, 0] = 200
     with pytest.raises(ValueError, match="query peak"):
         engine.ssm_features(CH, q, rows, bad, n_pairs)
+    from ann_solo_b200 import SoloError
+    bad = pairs.copy()
+    bad[1, 0, 1] = 120          # library peak index beyond the matched library spectrum: caught on the device
+    with pytest.raises(SoloError, match="outside its spectra"):
+        engine.ssm_features(CH, q, rows, bad, n_pairs)
 
 
 def test_staged_features_equal_oracle_on_a_fused_search(engine, oracle, synth, small_world):
