@@ -971,6 +971,26 @@ int solo_splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_
     });
 }
 
+int solo_mgf_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_identifier_bytes,
+                   int64_t *n_seq_bytes, char *errbuf, int errbuf_len) {
+    if (!path || !n_spectra || !n_peaks || !n_identifier_bytes || !n_seq_bytes) return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len,
+                            [&] { mgf_count(path, n_spectra, n_peaks, n_identifier_bytes, n_seq_bytes); });
+}
+
+int solo_mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_identifier_bytes, int64_t n_seq_bytes,
+                  double *prec_mz, int32_t *prec_charge, double *rt_seconds, uint8_t *is_decoy, int64_t *peak_offsets,
+                  double *mz, float *intensity, int64_t *identifier_offsets, char *identifiers, int64_t *seq_offsets,
+                  char *seqs, char *errbuf, int errbuf_len) {
+    if (!path || !prec_mz || !prec_charge || !rt_seconds || !is_decoy || !peak_offsets || !mz || !intensity ||
+        !identifier_offsets || !identifiers || !seq_offsets || !seqs)
+        return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len, [&] {
+        mgf_read(path, n_spectra, n_peaks, n_identifier_bytes, n_seq_bytes, prec_mz, prec_charge, rt_seconds, is_decoy,
+                 peak_offsets, mz, intensity, identifier_offsets, identifiers, seq_offsets, seqs);
+    });
+}
+
 int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity, const int64_t *offsets,
                          const double *prec_mz, const int32_t *prec_charge, int64_t n, const solo_process_params *p,
                          void *out_mz, float *out_intensity, int32_t *out_index, int32_t *out_count, uint8_t *out_valid) {

@@ -323,6 +323,11 @@ struct ProcessArgs {
     int32_t *err;            // [0]: spectra with more than K0_MAX_RAW peaks
 };
 void launch_process(solo_handle *h, const ProcessArgs &a, int mz_is_f64);
+// mgf_io.cu: MGF query files -> CSR arrays (host only)
+void mgf_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_title_bytes, int64_t *n_seq_bytes);
+void mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_title_bytes, int64_t n_seq_bytes,
+              double *prec_mz, int32_t *prec_charge, double *rt, uint8_t *is_decoy, int64_t *peak_off, double *mz,
+              float *inten, int64_t *title_off, char *titles, int64_t *seq_off, char *seqs);
 // splib_io.cu: SpectraST .splib -> CSR arrays (host only)
 void splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes);
 void splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes, uint32_t *id,

@@ -5,19 +5,25 @@ manager, but is built from ONE native pass over the file (csrc/splib_io.cu) and 
 charges to the device as processed peak stores (``charge_store``: K0, csrc/k0_process.cu) instead of
 one Python object per spectrum.
 
-Not mirrored: the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
+The query side: ``read_mgf`` / ``read_query_file`` (reference :868-938) over the native MGF parser
+(csrc/mgf_io.cu), plus ``read_mgf_store`` = the whole file as one raw peak store for K0.
+
+Not mirrored: ``.mzml`` / ``.mzxml`` query files (pyteomics XML readers), the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
 out of scope, the parsed library stays in host memory), ``.sptxt`` / ``.mgf`` libraries and decoy
 generation (``config.add_decoys``).
 """
 from __future__ import annotations
 
+import ctypes as C
+import math
 import os
 from typing import Iterator, Optional
 
 import numpy as np
 
+from . import _lib
 from .config import config
-from .parsers import _Annotation, read_splib
+from .parsers import _Annotation, _raise, read_splib
 from .spectrum import MsmsSpectrum, process_spectrum
 
 
@@ -133,3 +139,62 @@ class SpectralLibraryReader:
         out["is_decoy"] = sub["is_decoy"]
         self._processed[charge] = out
         return out
+
+
+# ---------------------------------------------------------------------- query files
+def read_mgf_store(filename: str) -> dict:
+    """Every spectrum of an MGF file as one RAW peak store (file order): mz float32 + mz64 float64
+    (ascending inside a spectrum), inten float32, off, prec_mz, prec_z (0 = no CHARGE line), rt (NaN = not
+    given), is_decoy, identifier (list of str), seq (list of str, '' = not given)."""
+    lib = _lib.load()
+    err = C.create_string_buffer(512)
+    n, npk, nid, nseq = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    path = os.fspath(filename).encode()
+    rc = lib.solo_mgf_count(path, C.byref(n), C.byref(npk), C.byref(nid), C.byref(nseq), err, len(err))
+    if rc:
+        _raise(rc, err)
+    n, npk, nid, nseq = n.value, npk.value, nid.value, nseq.value
+    out = dict(prec_mz=np.empty(n, np.float64), prec_z=np.empty(n, np.int32), rt=np.empty(n, np.float64),
+               is_decoy=np.empty(n, np.uint8), off=np.empty(n + 1, np.int64), mz64=np.empty(npk, np.float64),
+               inten=np.empty(npk, np.float32))
+    id_off, seq_off = np.empty(n + 1, np.int64), np.empty(n + 1, np.int64)
+    ids, seqs = np.empty(max(nid, 1), np.uint8), np.empty(max(nseq, 1), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.solo_mgf_read(path, n, npk, nid, nseq, p(out["prec_mz"]), p(out["prec_z"]), p(out["rt"]), p(out["is_decoy"]),
+                           p(out["off"]), p(out["mz64"]), p(out["inten"]), p(id_off), p(ids), p(seq_off), p(seqs), err,
+                           len(err))
+    if rc:
+        _raise(rc, err)
+    raw_ids, raw_seqs = ids.tobytes(), seqs.tobytes()
+    out["identifier"] = [raw_ids[id_off[i]:id_off[i + 1]].decode() for i in range(n)]
+    out["seq"] = [raw_seqs[seq_off[i]:seq_off[i + 1]].decode() for i in range(n)]
+    out["mz"] = out["mz64"].astype(np.float32)
+    out["valid"] = np.ones(n, np.uint8)
+    return out
+
+
+def read_mgf(filename: str) -> Iterator[MsmsSpectrum]:
+    """Reference reader.py:868-911: one MsmsSpectrum per entry, ``index`` 1-based, ``precursor_charge``
+    None without a CHARGE line, ``retention_time`` None without RTINSECONDS. SEQ is kept as written
+    (the reference rewrites MassIVE-KB modifications to ProForma, :837-866)."""
+    st = read_mgf_store(filename)
+    for i in range(len(st["prec_mz"])):
+        b, e = st["off"][i], st["off"][i + 1]
+        z = int(st["prec_z"][i])
+        rt = float(st["rt"][i])
+        s = MsmsSpectrum(st["identifier"][i], st["prec_mz"][i], z if z != 0 else None, st["mz64"][b:e].copy(),
+                         st["inten"][b:e].copy(), retention_time=None if math.isnan(rt) else rt,
+                         peptide=st["seq"][i] or None, is_decoy=bool(st["is_decoy"][i]))
+        s.index = i + 1
+        s.is_processed = False
+        yield s
+
+
+def read_query_file(filename: str) -> Iterator[MsmsSpectrum]:
+    """Reference reader.py:914-938."""
+    verify_extension([".mgf", ".mzml", ".mzxml"], filename)
+    _, ext = os.path.splitext(os.path.basename(filename))
+    if ext.lower() == ".mgf":
+        return read_mgf(filename)
+    raise NotImplementedError(f"{ext} query files need the reference's pyteomics readers (reader.py:659-835); "
+                              "only .mgf is read natively")

@@ -186,8 +186,11 @@ class SpectralLibrary:
 
     # ------------------------------------------------------------------ search
     def search(self, query_spectra) -> List[SpectrumSpectrumMatch]:
-        """Reference :193-260. ``query_spectra`` is an iterable of query spectrum objects (the
-        reference reads them from a file with reader.read_query_file, which is out of scope)."""
+        """Reference :193-260. ``query_spectra`` is a query file name (``.mgf``, read natively) like in the
+        reference, or an iterable of query spectrum objects."""
+        if isinstance(query_spectra, (str, os.PathLike)):   # the reference's signature: search(query_filename), :193-215
+            from .reader import read_query_file
+            query_spectra = read_query_file(os.fspath(query_spectra))
         by_charge = collections.defaultdict(list)
         for query_spectrum in query_spectra:
             if query_spectrum.precursor_charge is not None:

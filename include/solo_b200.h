@@ -232,6 +232,18 @@ int solo_splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_
                     uint8_t *peak_charge, int64_t *peptide_offsets, char *peptides, char *errbuf,
                     int errbuf_len);
 
+/* MGF query files: replaces reader.read_mgf (reader.py:868-911, pyteomics) for bulk ingestion of raw
+ * query spectra. Host code, no handle; same count / allocate / fill protocol. precursor_charge 0 = no
+ * CHARGE line (None in the reference); rt_seconds NaN = no RTINSECONDS; identifiers = TITLE, else
+ * SCAN(S), else the 1-based index; peaks come back m/z-ascending, m/z float64, intensity float32. */
+int solo_mgf_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_identifier_bytes,
+                   int64_t *n_seq_bytes, char *errbuf, int errbuf_len);
+int solo_mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_identifier_bytes,
+                  int64_t n_seq_bytes, double *prec_mz, int32_t *prec_charge, double *rt_seconds,
+                  uint8_t *is_decoy, int64_t *peak_offsets, double *mz, float *intensity,
+                  int64_t *identifier_offsets, char *identifiers, int64_t *seq_offsets, char *seqs,
+                  char *errbuf, int errbuf_len);
+
 /* ---- K6: SSM feature table for rescoring --------------------------------
  * Replaces utils._compute_ssm_features (utils.py:276-457): for every spectrum-spectrum match the 44
  * numeric columns that function derives from spectrum_similarity.SpectrumSimilarityCalculator(ssm) and
