@@ -101,3 +101,48 @@ def test_spectral_library_from_splib_file(engine, synth, tmp_path):
             SpectralLibrary(str(tmp_path / "human.mgf"), engine=engine)
     finally:
         config.update(dict(num_list=256, num_probe=128, num_candidates=1024))
+
+
+def test_search_takes_a_query_file_name(engine, synth, tmp_path):
+    """SpectralLibrary.search(query_filename) (reference spectral_library.py:193-215): raw MGF queries
+    are read natively, processed, and searched through the cascade; the identifications equal those
+    of the same raw spectra handed over as objects."""
+    from oracle import mgf_io
+    from ann_solo_b200.config import config
+    from ann_solo_b200.spectral_library import SpectralLibrary
+    from ann_solo_b200.spectrum import MsmsSpectrum
+    rng = np.random.default_rng(141)
+    lib = synth.make_library(2400, seed=141, decoy_seed=142)
+    queries = synth.make_queries(lib, 120, seed=143)
+    lib_path, mgf_path = str(tmp_path / "lib.splib"), str(tmp_path / "queries.mgf")
+    _write_raw_library(lib_path, lib, rng)
+    entries, objects = [], []
+    for i in range(120):
+        b, e = queries["off"][i], queries["off"][i + 1]
+        inten = (50 - np.argsort(np.argsort(-queries["inten"][b:e], kind="stable"), kind="stable")) * 100.0
+        n_noise = int(rng.integers(5, 30))
+        mz = np.concatenate([queries["mz"][b:e].astype(np.float64), rng.uniform(60.0, 1990.0, n_noise)])
+        it = np.concatenate([inten, rng.uniform(0.1, 0.009 * inten.max(), n_noise)])
+        order = np.argsort(mz, kind="stable")
+        z = int(queries["prec_z"][i])
+        entry = dict(title=f"q{i}", prec_mz=float(queries["prec_mz"][i]), mz=mz[order], intensity=it[order])
+        if i % 10:                      # every tenth query has no CHARGE line: searched as 2+ and 3+
+            entry["charge"] = f"{z}+"
+        entries.append(entry)
+        objects.append(MsmsSpectrum(f"q{i}", entry["prec_mz"], z if i % 10 else None, mz[order],
+                                    it[order].astype(np.float32)))
+    mgf_io.write_mgf(mgf_path, entries)
+    config.update(dict(num_list=16, num_probe=8, num_candidates=64, precursor_tolerance_mass=20.0,
+                       precursor_tolerance_mode="ppm", precursor_tolerance_mass_open=300.0,
+                       precursor_tolerance_mode_open="Da", fdr=0.05, mode="ann"))
+    try:
+        sl = SpectralLibrary(lib_path, engine=engine, train_iters=3)
+        from_file = {s.query_identifier: (s.library_identifier, s.search_engine_score) for s in sl.search(mgf_path)}
+        from_objects = {s.query_identifier: (s.library_identifier, s.search_engine_score) for s in sl.search(objects)}
+        assert from_file == from_objects and len(from_file) > 50
+        truth = queries["truth"]
+        correct = sum(1 for q, (lid, _) in from_file.items() if truth[int(q[1:])] >= 0 and
+                      int(lid) - 5000 == truth[int(q[1:])])
+        assert correct > 35
+    finally:
+        config.update(dict(num_list=256, num_probe=128, num_candidates=1024))
