@@ -209,7 +209,9 @@ def ssm_features(q_mz, q_int, l_mz, l_int, pairs, q_prec_mz: float, q_charge: in
     ul_t = l_int[np.intersect1d(lib_unmatched, top)]
     if keep.any():
         mq_t, ml_t = mq[keep], ml[keep]
-        f["cosine_top5"] = float((mq_t * ml_t).sum() / (math.sqrt((mq_t ** 2).sum()) * math.sqrt((ml_t ** 2).sum())))
+        with np.errstate(invalid="ignore", divide="ignore"):  # all-zero matched intensities: NaN, like the reference
+            f["cosine_top5"] = float(np.float64((mq_t * ml_t).sum()) /
+                                     np.float64(math.sqrt((mq_t ** 2).sum()) * math.sqrt((ml_t ** 2).sum())))
         f["frac_n_peaks_lib_top5"] = len(ml_t) / (len(ml_t) + len(ul_t))
         f["frac_int_lib_top5"] = ml_t.sum() / (ml_t.sum() + ul_t.sum())
         f["mse_mz_top5"] = ((q_mz[qi[keep]] - l_mz[li[keep]]) ** 2).sum() / len(ml_t)

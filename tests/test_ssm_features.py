@@ -147,3 +147,40 @@ def test_kendall_exact_and_asymptotic_against_scipy():
             want = scipy.stats.kendalltau(x, y)[1]
             assert sf.kendalltau_pvalue(x, y) == pytest.approx(want, rel=1e-10), n
     assert np.isnan(sf.kendalltau_pvalue([1.0], [2.0])) and np.isnan(sf.kendalltau_pvalue([1.0, 1.0], [2.0, 3.0]))
+
+
+def test_kernel_source_on_host_equals_oracle_on_random_ssms():
+    """Seeded random SSMs beyond the golden set: tiny spectra (fewer than five library peaks), single
+    matches, tied and zero intensities, up to 128 peaks — the kernel's source (host build) against the
+    float64 oracle."""
+    lib = _host_kernel()
+    rng = np.random.default_rng(99)
+    n_done = 0
+    for t in range(400):
+        nq = int(rng.integers(1, 129 if t % 40 == 0 else 60))
+        nl = int(rng.integers(1, 129 if t % 40 == 1 else 60))
+        q_mz = np.sort(rng.uniform(100, 1900, nq)).astype(np.float32 if t % 2 else np.float64)
+        l_mz = np.sort(rng.uniform(100, 1900, nl)).astype(np.float32)
+        if t % 3 == 0:      # ties (and zeros) inside the spectra; the top-5 cut kept free of ties
+            q_int = rng.integers(0, 6, nq).astype(np.float32)
+            l_int = rng.integers(1, 6, nl).astype(np.float32)
+            top = np.argsort(-l_int, kind="stable")[:6]
+            l_int[top] += np.arange(len(top), 0, -1, dtype=np.float32) * 10
+            if not q_int.any():
+                q_int[0] = 1
+        else:
+            q_int = rng.random(nq).astype(np.float32) + np.float32(0.01)
+            l_int = rng.random(nl).astype(np.float32) + np.float32(0.01)
+        q_int /= np.linalg.norm(q_int)
+        l_int /= np.linalg.norm(l_int)
+        m = int(rng.integers(1, min(nq, nl) + 1))
+        pairs = np.stack([rng.choice(nq, m, replace=False), rng.choice(nl, m, replace=False)], axis=1)
+        c = dict(q_mz=q_mz, q_int=q_int, l_mz=l_mz, l_int=l_int, pairs=pairs, q_prec=float(rng.uniform(300, 900)),
+                 q_z=int(rng.integers(1, 7)), l_prec=float(rng.uniform(300, 900)))
+        got = host_kernel_row(lib, c, seq_len=t % 31)
+        want = sf.ssm_features(q_mz, q_int, l_mz, l_int, pairs, c["q_prec"], c["q_z"], c["l_prec"], t % 31, BINS)
+        both_nan = np.isnan(got) & np.isnan(want)
+        np.testing.assert_allclose(np.where(both_nan, 0, got), np.where(both_nan, 0, want), rtol=1e-9, atol=1e-11,
+                                   err_msg=f"case {t}: nq {nq} nl {nl} m {m}")
+        n_done += 1
+    assert n_done == 400
