@@ -328,6 +328,10 @@ void mgf_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *
 void mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_title_bytes, int64_t n_seq_bytes,
               double *prec_mz, int32_t *prec_charge, double *rt, uint8_t *is_decoy, int64_t *peak_off, double *mz,
               float *inten, int64_t *title_off, char *titles, int64_t *seq_off, char *seqs);
+// mzml_io.cu: mzML query files -> CSR arrays (host only)
+void mzml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped);
+void mzml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index, double *prec_mz,
+               int32_t *prec_charge, double *rt, int64_t *peak_off, double *mz, float *inten);
 // splib_io.cu: SpectraST .splib -> CSR arrays (host only)
 void splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes);
 void splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes, uint32_t *id,

@@ -244,6 +244,17 @@ int solo_mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t 
                   int64_t *identifier_offsets, char *identifiers, int64_t *seq_offsets, char *seqs,
                   char *errbuf, int errbuf_len);
 
+/* mzML query files: replaces reader.read_mzml / _parse_spectrum_mzml (reader.py:659-741, pyteomics + lxml).
+ * Only MS level 2 spectra are returned; scan_nr = the integer after "scan=" (else "index=") in the spectrum
+ * id (the reference's identifier, as str), index = position among ALL spectra of the file; spectra the
+ * reference would skip with a warning (no scan/index number, no selected ion) are counted in n_skipped.
+ * 32/64-bit float arrays, uncompressed or zlib. Same count / allocate / fill protocol, host code. */
+int solo_mzml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped, char *errbuf,
+                    int errbuf_len);
+int solo_mzml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index,
+                   double *prec_mz, int32_t *prec_charge, double *rt, int64_t *peak_offsets, double *mz,
+                   float *intensity, char *errbuf, int errbuf_len);
+
 /* ---- K6: SSM feature table for rescoring --------------------------------
  * Replaces utils._compute_ssm_features (utils.py:276-457): for every spectrum-spectrum match the 44
  * numeric columns that function derives from spectrum_similarity.SpectrumSimilarityCalculator(ssm) and
