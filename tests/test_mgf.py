@@ -81,9 +81,9 @@ def test_read_mgf_objects_like_the_reference(tmp_path):
         read_query_file(str(tmp_path / "missing.mgf"))
     with pytest.raises(FileNotFoundError):
         read_query_file(str(tmp_path / "small.txt"))
-    (tmp_path / "x.mzml").write_text("<mzML/>")
+    (tmp_path / "x.mzxml").write_text("<mzXML/>")
     with pytest.raises(NotImplementedError):
-        read_query_file(str(tmp_path / "x.mzml"))
+        read_query_file(str(tmp_path / "x.mzxml"))
 
 
 def test_errors(tmp_path):
