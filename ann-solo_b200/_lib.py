@@ -95,6 +95,8 @@ SYMBOLS = {
                                 C.c_char_p, C.c_int]),
     "solo_mzml_count": (C.c_int, [C.c_char_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.c_char_p, C.c_int]),
     "solo_mzml_read": (C.c_int, [C.c_char_p, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, C.c_int]),
+    "solo_mzxml_count": (C.c_int, [C.c_char_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.c_char_p, C.c_int]),
+    "solo_mzxml_read": (C.c_int, [C.c_char_p, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, C.c_int]),
     "solo_ssm_feature_name": (C.c_char_p, [C.c_int]),
     "solo_ssm_features": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp]),

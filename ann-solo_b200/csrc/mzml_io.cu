@@ -365,7 +365,157 @@ void walk_mzml(const XmlFile &f, const char *path, MzmlSink *out, int64_t &n_spe
     if (out) out->peak_off[n_spec] = n_peaks;
 }
 
+// ---------------------------------------------------------------- mzXML (reference reader.py:743-811)
+// <scan num=".." msLevel=".." retentionTime="PT..S"> <precursorMz precursorCharge="..">m/z</precursorMz>
+// <peaks precision="32|64" byteOrder="network" contentType="m/z-int" compressionType="none|zlib">base64</peaks>
+// [nested <scan> children] </scan>. A scan's own precursorMz / peaks precede its children, so they are the
+// ones found before the next <scan start tag. identifier = str(int(num)); index = position among all scans.
+double be_float(const uint8_t *p, int bits) {
+    if (bits == 64) {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+        double d;
+        memcpy(&d, &v, 8);
+        return d;
+    }
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) v = (v << 8) | p[i];
+    float f;
+    memcpy(&f, &v, 4);
+    return (double)f;
+}
+
+void walk_mzxml(const XmlFile &f, const char *path, MzmlSink *out, int64_t &n_spec, int64_t &n_peaks, int64_t &n_skipped) {
+    n_spec = n_peaks = n_skipped = 0;
+    const char *end = f.p + f.size;
+    long long index = 0;
+    std::vector<uint8_t> raw, tmp;
+    std::vector<double> mz, inten;
+    std::vector<int32_t> order;
+    auto next_scan = [&](const char *from) -> const char * {
+        for (const char *q = from; q && (q = find(q, end, "<scan")) != nullptr; q += 5) {
+            const char c = q + 5 < end ? q[5] : 0;
+            if (c == ' ' || c == '\t' || c == '\n' || c == '\r') return q;
+        }
+        return nullptr;
+    };
+    for (const char *sb = f.size ? next_scan(f.p) : nullptr; sb;) {
+        const char *tag_end = (const char *)memchr(sb, '>', (size_t)(end - sb));
+        SOLO_REQUIRE(tag_end, SOLO_EINVAL, "'%s': unterminated <scan> tag", path);
+        const char *nxt = next_scan(tag_end);
+        const char *se = nxt ? nxt : end;   // this scan's own children end before the next <scan
+        const long long this_index = index++;
+        const char *vb, *ve;
+        long long level = -1, num = 0;
+        if (attr(sb, tag_end, "msLevel", vb, ve)) to_int(vb, ve, level);
+        const bool id_ok = attr(sb, tag_end, "num", vb, ve) && to_int(vb, ve, num);
+        double rt = NAN;
+        if (attr(sb, tag_end, "retentionTime", vb, ve) && ve - vb > 3 && vb[0] == 'P' && vb[1] == 'T' && ve[-1] == 'S') {
+            double sec;
+            if (to_double(vb + 2, ve - 1, sec)) rt = sec / 60.0;   // xsd:duration in seconds -> minutes
+        }
+        sb = nxt;
+        if (level != 2) continue;                                   // reader.py:761
+        const char *pm = find(tag_end, se, "<precursorMz");
+        const char *pk = find(tag_end, se, "<peaks");
+        if (!id_ok || !pm) {
+            ++n_skipped;
+            continue;
+        }
+        const char *pm_gt = (const char *)memchr(pm, '>', (size_t)(se - pm));
+        const char *pm_close = pm_gt ? find(pm_gt, se, "</precursorMz>") : nullptr;
+        double prec_mz = 0.0;
+        SOLO_REQUIRE(pm_close && to_double(pm_gt + 1, pm_close, prec_mz), SOLO_EINVAL,
+                     "'%s' scan %lld: precursorMz is not a number", path, num);
+        long long charge = 0;
+        if (attr(pm, pm_gt, "precursorCharge", vb, ve)) to_int(vb, ve, charge);
+        SOLO_REQUIRE(pk, SOLO_EINVAL, "'%s' scan %lld: no <peaks>", path, num);
+        const char *pk_gt = (const char *)memchr(pk, '>', (size_t)(se - pk));
+        SOLO_REQUIRE(pk_gt, SOLO_EINVAL, "'%s' scan %lld: unterminated <peaks>", path, num);
+        long long precision = 32;
+        if (attr(pk, pk_gt, "precision", vb, ve)) to_int(vb, ve, precision);
+        SOLO_REQUIRE(precision == 32 || precision == 64, SOLO_EINVAL, "'%s' scan %lld: precision %lld", path, num, precision);
+        const bool zl = attr_is(pk, pk_gt, "compressionType", "zlib");
+        SOLO_REQUIRE(zl || !attr(pk, pk_gt, "compressionType", vb, ve) || attr_is(pk, pk_gt, "compressionType", "none"),
+                     SOLO_EINVAL, "'%s' scan %lld: unsupported compressionType", path, num);
+        SOLO_REQUIRE(!attr(pk, pk_gt, "byteOrder", vb, ve) || attr_is(pk, pk_gt, "byteOrder", "network"), SOLO_EINVAL,
+                     "'%s' scan %lld: byteOrder must be network", path, num);
+        const uint8_t *data = nullptr;
+        size_t nbytes = 0;
+        if (pk_gt[-1] != '/') {
+            const char *pk_close = find(pk_gt, se, "</peaks>");
+            SOLO_REQUIRE(pk_close, SOLO_EINVAL, "'%s' scan %lld: <peaks> without </peaks>", path, num);
+            SOLO_REQUIRE(base64_decode(pk_gt + 1, pk_close, raw), SOLO_EINVAL, "'%s' scan %lld: malformed base64", path, num);
+            data = raw.data();
+            nbytes = raw.size();
+            if (zl && nbytes) {
+                uncompress_fn un = zlib_uncompress();
+                SOLO_REQUIRE(un != nullptr, SOLO_ESTATE, "'%s' holds zlib-compressed peaks but libz.so.1 cannot be loaded", path);
+                size_t cap = nbytes * 8 + 1024;
+                for (int attempt = 0;; ++attempt) {
+                    tmp.resize(cap);
+                    unsigned long got = (unsigned long)cap;
+                    const int rc = un(tmp.data(), &got, raw.data(), (unsigned long)nbytes);
+                    if (rc == 0) {
+                        data = tmp.data();
+                        nbytes = got;
+                        break;
+                    }
+                    SOLO_REQUIRE(rc == -5 && attempt < 8, SOLO_EINVAL, "'%s' scan %lld: zlib error %d", path, num, rc);
+                    cap *= 4;
+                }
+            }
+        }
+        const size_t pair = (size_t)precision / 4;   // bytes per (m/z, intensity) pair
+        SOLO_REQUIRE(nbytes % pair == 0, SOLO_EINVAL, "'%s' scan %lld: %zu bytes is not a whole number of peaks", path, num, nbytes);
+        const long long n = (long long)(nbytes / pair);
+        if (out) {
+            mz.resize((size_t)n);
+            inten.resize((size_t)n);
+            for (long long i = 0; i < n; ++i) {
+                mz[i] = be_float(data + pair * i, (int)precision);
+                inten[i] = be_float(data + pair * i + pair / 2, (int)precision);
+            }
+            out->scan_nr[n_spec] = num;
+            out->index[n_spec] = (int32_t)this_index;
+            out->prec_mz[n_spec] = prec_mz;
+            out->prec_charge[n_spec] = (int32_t)charge;
+            out->rt[n_spec] = rt;
+            out->peak_off[n_spec] = n_peaks;
+            order.resize((size_t)n);
+            std::iota(order.begin(), order.end(), 0);
+            if (!std::is_sorted(mz.begin(), mz.end()))
+                std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return mz[a] < mz[b]; });
+            for (long long i = 0; i < n; ++i) {
+                out->mz[n_peaks + i] = mz[order[i]];
+                out->inten[n_peaks + i] = (float)inten[order[i]];
+            }
+        }
+        n_peaks += n;
+        ++n_spec;
+    }
+    if (out) out->peak_off[n_spec] = n_peaks;
+}
+
 }  // namespace
+
+void mzxml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped) {
+    XmlFile f;
+    f.open(path);
+    walk_mzxml(f, path, nullptr, *n_spectra, *n_peaks, *n_skipped);
+}
+
+void mzxml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index, double *prec_mz,
+                int32_t *prec_charge, double *rt, int64_t *peak_off, double *mz, float *inten) {
+    XmlFile f;
+    f.open(path);
+    int64_t a, b, c;
+    walk_mzxml(f, path, nullptr, a, b, c);
+    SOLO_REQUIRE(a == n_spectra && b == n_peaks, SOLO_EINVAL, "'%s' holds %lld MS2 scans / %lld peaks, the buffers were sized for %lld / %lld",
+                 path, (long long)a, (long long)b, (long long)n_spectra, (long long)n_peaks);
+    MzmlSink s{scan_nr, index, prec_mz, prec_charge, rt, peak_off, mz, inten};
+    walk_mzxml(f, path, &s, a, b, c);
+}
 
 void mzml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped) {
     XmlFile f;

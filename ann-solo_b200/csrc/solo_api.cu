@@ -1007,6 +1007,22 @@ int solo_mzml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t
     });
 }
 
+int solo_mzxml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped, char *errbuf,
+                     int errbuf_len) {
+    if (!path || !n_spectra || !n_peaks || !n_skipped) return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len, [&] { mzxml_count(path, n_spectra, n_peaks, n_skipped); });
+}
+
+int solo_mzxml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index, double *prec_mz,
+                    int32_t *prec_charge, double *rt, int64_t *peak_offsets, double *mz, float *intensity, char *errbuf,
+                    int errbuf_len) {
+    if (!path || !scan_nr || !index || !prec_mz || !prec_charge || !rt || !peak_offsets || !mz || !intensity)
+        return SOLO_EINVAL;
+    return guarded_nohandle(errbuf, errbuf_len, [&] {
+        mzxml_read(path, n_spectra, n_peaks, scan_nr, index, prec_mz, prec_charge, rt, peak_offsets, mz, intensity);
+    });
+}
+
 int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity, const int64_t *offsets,
                          const double *prec_mz, const int32_t *prec_charge, int64_t n, const solo_process_params *p,
                          void *out_mz, float *out_intensity, int32_t *out_index, int32_t *out_count, uint8_t *out_valid) {

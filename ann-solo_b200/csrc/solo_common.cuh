@@ -332,6 +332,9 @@ void mgf_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_ti
 void mzml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped);
 void mzml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index, double *prec_mz,
                int32_t *prec_charge, double *rt, int64_t *peak_off, double *mz, float *inten);
+void mzxml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped);
+void mzxml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index, double *prec_mz,
+                int32_t *prec_charge, double *rt, int64_t *peak_off, double *mz, float *inten);
 // splib_io.cu: SpectraST .splib -> CSR arrays (host only)
 void splib_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_peptide_bytes);
 void splib_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t n_peptide_bytes, uint32_t *id,

@@ -8,9 +8,9 @@ one Python object per spectrum.
 The query side: ``read_mgf`` / ``read_query_file`` (reference :868-938) over the native MGF parser
 (csrc/mgf_io.cu), plus ``read_mgf_store`` = the whole file as one raw peak store for K0.
 
-``read_mzml`` / ``read_mzml_store`` do the same for mzML (csrc/mzml_io.cu).
+``read_mzml`` / ``read_mzxml`` (+ ``_store`` variants) do the same for mzML and mzXML (csrc/mzml_io.cu).
 
-Not mirrored: ``.mzxml`` query files, the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
+Not mirrored: the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
 out of scope, the parsed library stays in host memory), ``.sptxt`` / ``.mgf`` libraries and decoy
 generation (``config.add_decoys``).
 """
@@ -192,16 +192,14 @@ def read_mgf(filename: str) -> Iterator[MsmsSpectrum]:
         yield s
 
 
-def read_mzml_store(filename: str) -> dict:
-    """Every MS2 spectrum of an mzML file as one RAW peak store: mz float32 + mz64 float64 (ascending),
-    inten float32, off, prec_mz, prec_z (0 = no charge cvParam), rt (as written; NaN = absent), scan_nr,
-    index (position among all spectra of the file), identifier (list of str = str(scan_nr)), n_skipped
-    (MS2 spectra the reference would skip with a warning)."""
+def _read_xml_store(filename: str, kind: str) -> dict:
     lib = _lib.load()
+    count, read = (lib.solo_mzml_count, lib.solo_mzml_read) if kind == "mzml" else (lib.solo_mzxml_count,
+                                                                                     lib.solo_mzxml_read)
     err = C.create_string_buffer(512)
     n, npk, nskip = C.c_int64(), C.c_int64(), C.c_int64()
     path = os.fspath(filename).encode()
-    rc = lib.solo_mzml_count(path, C.byref(n), C.byref(npk), C.byref(nskip), err, len(err))
+    rc = count(path, C.byref(n), C.byref(npk), C.byref(nskip), err, len(err))
     if rc:
         _raise(rc, err)
     n, npk = n.value, npk.value
@@ -209,8 +207,8 @@ def read_mzml_store(filename: str) -> dict:
                prec_z=np.empty(n, np.int32), rt=np.empty(n, np.float64), off=np.empty(n + 1, np.int64),
                mz64=np.empty(npk, np.float64), inten=np.empty(npk, np.float32))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.solo_mzml_read(path, n, npk, p(out["scan_nr"]), p(out["index"]), p(out["prec_mz"]), p(out["prec_z"]),
-                            p(out["rt"]), p(out["off"]), p(out["mz64"]), p(out["inten"]), err, len(err))
+    rc = read(path, n, npk, p(out["scan_nr"]), p(out["index"]), p(out["prec_mz"]), p(out["prec_z"]),
+              p(out["rt"]), p(out["off"]), p(out["mz64"]), p(out["inten"]), err, len(err))
     if rc:
         _raise(rc, err)
     out["identifier"] = [str(s) for s in out["scan_nr"]]
@@ -220,10 +218,20 @@ def read_mzml_store(filename: str) -> dict:
     return out
 
 
-def read_mzml(source: str) -> Iterator[MsmsSpectrum]:
-    """Reference reader.py:659-741: MS level 2 spectra only, identifier = str(scan number), ``index`` =
-    position among all spectra of the file, ``precursor_charge`` None without a charge cvParam."""
-    st = read_mzml_store(source)
+def read_mzml_store(filename: str) -> dict:
+    """Every MS2 spectrum of an mzML file as one RAW peak store: mz float32 + mz64 float64 (ascending),
+    inten float32, off, prec_mz, prec_z (0 = no charge cvParam), rt (as written; NaN = absent), scan_nr,
+    index (position among all spectra of the file), identifier (list of str = str(scan_nr)), n_skipped
+    (MS2 spectra the reference would skip with a warning)."""
+    return _read_xml_store(filename, "mzml")
+
+
+def read_mzxml_store(filename: str) -> dict:
+    """The same for mzXML (rt in minutes from the xsd:duration, prec_z 0 = no precursorCharge)."""
+    return _read_xml_store(filename, "mzxml")
+
+
+def _spectra_of(st: dict) -> Iterator[MsmsSpectrum]:
     for i in range(len(st["prec_mz"])):
         b, e = st["off"][i], st["off"][i + 1]
         z = int(st["prec_z"][i])
@@ -235,6 +243,17 @@ def read_mzml(source: str) -> Iterator[MsmsSpectrum]:
         yield s
 
 
+def read_mzml(source: str) -> Iterator[MsmsSpectrum]:
+    """Reference reader.py:659-741: MS level 2 spectra only, identifier = str(scan number), ``index`` =
+    position among all spectra of the file, ``precursor_charge`` None without a charge cvParam."""
+    return _spectra_of(read_mzml_store(source))
+
+
+def read_mzxml(source: str) -> Iterator[MsmsSpectrum]:
+    """Reference reader.py:743-811."""
+    return _spectra_of(read_mzxml_store(source))
+
+
 def read_query_file(filename: str) -> Iterator[MsmsSpectrum]:
     """Reference reader.py:914-938."""
     verify_extension([".mgf", ".mzml", ".mzxml"], filename)
@@ -243,5 +262,4 @@ def read_query_file(filename: str) -> Iterator[MsmsSpectrum]:
         return read_mgf(filename)
     if ext.lower() == ".mzml":
         return read_mzml(filename)
-    raise NotImplementedError(f"{ext} query files need the reference's pyteomics reader (reader.py:743-811); "
-                              ".mgf and .mzml are read natively")
+    return read_mzxml(filename)

@@ -255,6 +255,16 @@ int solo_mzml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t
                    double *prec_mz, int32_t *prec_charge, double *rt, int64_t *peak_offsets, double *mz,
                    float *intensity, char *errbuf, int errbuf_len);
 
+/* mzXML query files: replaces reader.read_mzxml / _parse_spectrum_mzxml (reader.py:743-811). Same
+ * outputs and protocol as the mzML pair: scan_nr = int(scan num), index = position among all scans
+ * (nested ones in document order), rt in minutes from the xsd:duration, network-order 32/64-bit peaks,
+ * uncompressed or zlib. */
+int solo_mzxml_count(const char *path, int64_t *n_spectra, int64_t *n_peaks, int64_t *n_skipped, char *errbuf,
+                     int errbuf_len);
+int solo_mzxml_read(const char *path, int64_t n_spectra, int64_t n_peaks, int64_t *scan_nr, int32_t *index,
+                    double *prec_mz, int32_t *prec_charge, double *rt, int64_t *peak_offsets, double *mz,
+                    float *intensity, char *errbuf, int errbuf_len);
+
 /* ---- K6: SSM feature table for rescoring --------------------------------
  * Replaces utils._compute_ssm_features (utils.py:276-457): for every spectrum-spectrum match the 44
  * numeric columns that function derives from spectrum_similarity.SpectrumSimilarityCalculator(ssm) and

@@ -111,3 +111,62 @@ def read_mzml(path: str) -> List[dict]:
                         rt=float(scv["MS:1000016"]) if "MS:1000016" in scv else math.nan,
                         mz=arrays["mz"][order], inten=arrays["inten"].astype(np.float32)[order]))
     return out
+
+
+# ---------------------------------------------------------------------- mzXML
+def write_mzxml(path: str, scans: List[dict]) -> None:
+    """scans: dicts with num, ms_level, mz, intensity and optionally prec_mz, charge, rt (seconds),
+    precision (32/64), zlib (bool), children (list of scans nested inside this one, as mzXML does for
+    the MS2 scans of a survey scan)."""
+    def emit(s, out):
+        prec = s.get("precision", 32)
+        inter = np.empty(2 * len(s["mz"]), ">f8" if prec == 64 else ">f4")
+        inter[0::2] = s["mz"]
+        inter[1::2] = s["intensity"]
+        raw = inter.tobytes()
+        comp = "none"
+        if s.get("zlib"):
+            raw = zlib.compress(raw)
+            comp = "zlib"
+        rt = f' retentionTime="PT{s["rt"]!r}S"' if "rt" in s else ""
+        out.append(f'<scan num="{s["num"]}" msLevel="{s["ms_level"]}" peaksCount="{len(s["mz"])}"{rt}>')
+        if "prec_mz" in s:
+            z = f' precursorCharge="{s["charge"]}"' if "charge" in s else ""
+            out.append(f'<precursorMz precursorIntensity="1234.5"{z}>{s["prec_mz"]!r}</precursorMz>')
+        out.append(f'<peaks precision="{prec}" byteOrder="network" contentType="m/z-int" compressionType="{comp}" '
+                   f'compressedLen="{len(raw) if s.get("zlib") else 0}">{base64.b64encode(raw).decode()}</peaks>')
+        for child in s.get("children", ()):
+            emit(child, out)
+        out.append("</scan>")
+
+    out = ['<?xml version="1.0" encoding="ISO-8859-1"?>', '<mzXML xmlns="http://sashimi.sourceforge.net/schema_revision/mzXML_3.2">',
+           '<msRun scanCount="0">']
+    for s in scans:
+        emit(s, out)
+    out += ["</msRun>", "</mzXML>"]
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+
+
+def read_mzxml(path: str) -> List[dict]:
+    ns = "{http://sashimi.sourceforge.net/schema_revision/mzXML_3.2}"
+    out = []
+    root = ET.parse(path).getroot()
+    for index, sc in enumerate(root.iter(ns + "scan")):       # document order, nested scans included
+        if int(sc.get("msLevel", -1)) != 2:
+            continue
+        pm = sc.find(ns + "precursorMz")
+        if pm is None:
+            continue
+        pk = sc.find(ns + "peaks")
+        raw = base64.b64decode(pk.text or "")
+        if pk.get("compressionType") == "zlib" and raw:
+            raw = zlib.decompress(raw)
+        a = np.frombuffer(raw, ">f8" if pk.get("precision") == "64" else ">f4").astype(np.float64)
+        mz, inten = a[0::2], a[1::2]
+        order = np.argsort(mz, kind="stable")
+        rt = sc.get("retentionTime")
+        out.append(dict(identifier=str(int(sc.get("num"))), index=index, prec_mz=float(pm.text),
+                        prec_z=int(pm.get("precursorCharge", 0)), rt=float(rt[2:-1]) / 60.0 if rt else math.nan,
+                        mz=mz[order], inten=inten.astype(np.float32)[order]))
+    return out

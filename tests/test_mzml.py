@@ -87,8 +87,7 @@ def test_read_mzml_objects_like_the_reference(tmp_path):
         assert s.mz.dtype == np.float64 and s.intensity.dtype == np.float32 and len(s.mz) == 8
     assert len(list(read_query_file(p))) == 2
     (tmp_path / "x.mzxml").write_text("<mzXML/>")
-    with pytest.raises(NotImplementedError):
-        read_query_file(str(tmp_path / "x.mzxml"))
+    assert list(read_query_file(str(tmp_path / "x.mzxml"))) == []
 
 
 def test_errors(tmp_path):
@@ -112,3 +111,48 @@ def test_errors(tmp_path):
         read_mzml_store(p)
     open(p, "w").write("")
     assert len(read_mzml_store(p)["prec_mz"]) == 0
+
+
+def test_mzxml_scanner_equals_oracle_reader(tmp_path):
+    """reference reader.py:743-811; MS2 scans nested inside their survey scan, as mzXML writes them."""
+    from ann_solo_b200.reader import read_mzxml, read_mzxml_store, read_query_file
+    rng = np.random.default_rng(8)
+    scans, num = [], 0
+
+    def ms2():
+        nonlocal num
+        num += 1
+        k = int(rng.integers(0, 70))
+        s = dict(num=num, ms_level=2, mz=np.sort(rng.uniform(50, 2000, k)), intensity=rng.gamma(0.7, 1000.0, k),
+                 prec_mz=float(rng.uniform(300, 1500)), precision=64 if num % 2 else 32, zlib=num % 3 == 0)
+        if num % 4:
+            s["charge"] = int(rng.integers(1, 5))
+        if num % 5:
+            s["rt"] = float(rng.uniform(0, 7200))
+        if num == 6:
+            del s["prec_mz"]                          # MS2 without precursorMz: skipped
+        if num == 8:
+            s["mz"] = s["mz"][::-1].copy()
+        return s
+
+    for _ in range(5):
+        num += 1
+        survey = dict(num=num, ms_level=1, mz=np.sort(rng.uniform(300, 1500, 20)), intensity=rng.random(20), rt=1.0)
+        survey["children"] = [ms2() for _ in range(3)]
+        scans.append(survey)
+    scans.append(ms2())                               # a top-level MS2 scan
+    p = str(tmp_path / "run.mzxml")
+    mzml_io.write_mzxml(p, scans)
+    want = mzml_io.read_mzxml(p)
+    got = read_mzxml_store(p)
+    assert len(want) == len(got["prec_mz"]) == 15 and got["n_skipped"] == 1
+    for i, w in enumerate(want):
+        b, e = got["off"][i], got["off"][i + 1]
+        assert got["identifier"][i] == w["identifier"] and got["index"][i] == w["index"]
+        assert got["prec_mz"][i] == w["prec_mz"] and got["prec_z"][i] == w["prec_z"]
+        assert (math.isnan(got["rt"][i]) and math.isnan(w["rt"])) or got["rt"][i] == pytest.approx(w["rt"], rel=1e-15)
+        assert np.array_equal(got["mz64"][b:e], w["mz"]) and np.array_equal(got["inten"][b:e], w["inten"])
+    objs = list(read_mzxml(p))
+    assert [o.identifier for o in objs] == [w["identifier"] for w in want]
+    assert objs[0].index == 1 and objs[0].mz.dtype == np.float64       # the survey scan is index 0
+    assert len(list(read_query_file(p))) == 15
