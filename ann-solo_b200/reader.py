@@ -11,8 +11,8 @@ The query side: ``read_mgf`` / ``read_query_file`` (reference :868-938) over the
 ``read_mzml`` / ``read_mzxml`` (+ ``_store`` variants) do the same for mzML and mzXML (csrc/mzml_io.cu).
 
 Not mirrored: the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
-out of scope, the parsed library stays in host memory), ``.sptxt`` / ``.mgf`` libraries and decoy
-generation (``config.add_decoys``).
+out of scope, the parsed library stays in host memory), ``.sptxt`` libraries and decoy generation
+(``config.add_decoys``). ``.mgf`` libraries (MassIVE-KB style, SEQ= lines) go through the native MGF parser.
 """
 from __future__ import annotations
 
@@ -42,7 +42,7 @@ def verify_extension(supported_extensions, filename: str) -> None:
 class SpectralLibraryReader:
     """Read spectra from a SpectraST ``.splib`` spectral library (reference reader.py:29-437)."""
 
-    _supported_extensions = [".splib"]
+    _supported_extensions = [".splib", ".mgf"]
     is_recreated = False
 
     def __init__(self, filename: str, config_hash: Optional[str] = None, engine=None) -> None:
@@ -50,9 +50,13 @@ class SpectralLibraryReader:
         self._config_hash = config_hash
         self._engine = engine
         verify_extension(self._supported_extensions, filename)
-        st = read_splib(filename)
+        if os.path.splitext(filename)[1].lower() == ".mgf":
+            st = _mgf_library_store(filename)                        # reference :283-284 read_mgf as a library
+            self._ids = np.array(st["id"])
+        else:
+            st = read_splib(filename)
+            self._ids = np.array([str(i) for i in st["id"]])        # parsers.pyx:145 str(identifier)
         self._store = st
-        self._ids = np.array([str(i) for i in st["id"]])            # parsers.pyx:145 str(identifier)
         self._row_of = {ident: r for r, ident in enumerate(self._ids.tolist())}
         self.spec_info = {"charge": {}}
         self._rows = {}
@@ -141,6 +145,37 @@ class SpectralLibraryReader:
         out["is_decoy"] = sub["is_decoy"]
         self._processed[charge] = out
         return out
+
+
+# ---------------------------------------------------------------------- MGF libraries (MassIVE-KB style)
+def _leading_substitute_pattern(match) -> str:
+    # reference reader.py:814-835
+    if match.group(1) and match.group(2):
+        return "[{}]?[{}]-{:s}".format(match.group(1), match.group(2), match.group(3))
+    if match.group(1):
+        return "[{}]-{}".format(match.group(1), match.group(3))
+    return match.group(0)
+
+
+def _mgf_seq_to_proforma(peptide: str) -> str:
+    """Reference reader.py:837-866: MassIVE-KB sequence ('+42.011AC+57.021K') to ProForma."""
+    import re
+    formatted = re.sub(r"([A-Z])([+-]?\d+\.\d+)", r"\1[\2]", peptide)
+    return re.sub(r"([+-]?[\d.]+)([+-]?[\d.]+)?([A-Za-z]+)", _leading_substitute_pattern, formatted)
+
+
+def _mgf_library_store(filename: str) -> dict:
+    """An MGF spectral library as the raw peak store the ``.splib`` path produces: identifier = TITLE /
+    SCAN / index, peptide = ProForma of SEQ, no fragment annotations (reference :906-909). Entries
+    without a CHARGE line cannot be assigned to a precursor charge and are refused."""
+    st = read_mgf_store(filename)
+    if (st["prec_z"] <= 0).any():
+        bad = int(np.flatnonzero(st["prec_z"] <= 0)[0])
+        raise ValueError(f"library spectrum {st['identifier'][bad]!r} of {filename} has no (positive) CHARGE")
+    st["id"] = st.pop("identifier")
+    st["peptide"] = [_mgf_seq_to_proforma(q) if q else None for q in st.pop("seq")]
+    st["chg"] = np.zeros(len(st["mz"]), np.uint8)
+    return st
 
 
 # ---------------------------------------------------------------------- query files

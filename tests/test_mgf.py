@@ -99,3 +99,36 @@ def test_errors(tmp_path):
         read_mgf_store(str(p))
     p.write_text("")
     assert len(read_mgf_store(str(p))["prec_mz"]) == 0
+
+
+def test_mgf_as_a_spectral_library(tmp_path):
+    """reference reader.py:34 (_supported_extensions) / :283-284: an MGF file as the library; the reader
+    surface (spec_info per charge in file order, raw spectra, ProForma peptides) needs no GPU."""
+    from ann_solo_b200.reader import SpectralLibraryReader, _mgf_seq_to_proforma
+    # reference reader.py:837-866
+    assert _mgf_seq_to_proforma("PEPTIDEK") == "PEPTIDEK"
+    assert _mgf_seq_to_proforma("AC+57.021DM+15.995K") == "AC[+57.021]DM[+15.995]K"
+    assert _mgf_seq_to_proforma("+42.011ACDK") == "[+42.011]-ACDK"
+    rng = np.random.default_rng(3)
+    entries = []
+    for i in range(12):
+        k = int(rng.integers(12, 40))
+        entries.append(dict(title=f"lib{i}", seq=["PEPTIDEK", "AC+57.021DK", "+42.011LESLIEK"][i % 3],
+                            prec_mz=float(rng.uniform(300, 900)), charge=f"{2 + i % 2}+",
+                            mz=np.sort(rng.uniform(100, 1500, k)), intensity=rng.gamma(0.7, 1000.0, k), decoy=i % 4 == 0))
+    p = str(tmp_path / "lib.mgf")
+    mgf_io.write_mgf(p, entries)
+    r = SpectralLibraryReader(p, "0123456789")
+    assert sorted(r.spec_info["charge"]) == [2, 3]
+    assert r.spec_info["charge"][2]["id"].tolist() == [f"lib{i}" for i in range(0, 12, 2)]
+    assert r.spec_info["charge"][3]["precursor_mz"].dtype == np.float32
+    assert np.array_equal(r.spec_info["charge"][3]["precursor_mz"],
+                          np.array([e["prec_mz"] for e in entries[1::2]], np.float32))
+    s = r.read_spectrum("lib4")
+    assert s.peptide == "AC[+57.021]DK" and s.is_decoy and s.precursor_charge == 2 and not s.is_processed
+    assert np.array_equal(s.mz, entries[4]["mz"].astype(np.float32)) and all(a is None for a in s.annotation)
+    assert [x.identifier for x in r.read_all_spectra()] == [f"lib{i}" for i in range(12)]
+    del entries[5]["charge"]
+    mgf_io.write_mgf(p, entries)
+    with pytest.raises(ValueError, match="CHARGE"):
+        SpectralLibraryReader(p)
