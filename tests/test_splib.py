@@ -79,3 +79,33 @@ def test_errors(tmp_path):
     open(p, "wb").write(raw[:offsets[-1] + 9])   # inside the last spectrum's name line: no precursor m/z follows
     with pytest.raises(ValueError, match="truncated|claims|malformed"):
         parsers.read_splib(p)
+
+
+def test_spectral_library_reader_surface_needs_no_gpu(tmp_path):
+    """reader.SpectralLibraryReader over a .splib: spec_info (reference reader.py:180-189), raw
+    read_spectrum / read_all_spectra, errors — the parts that never touch the device."""
+    from ann_solo_b200.reader import SpectralLibraryReader
+    specs = _library(40, seed=6)
+    p = str(tmp_path / "lib.splib")
+    splib_io.write_splib(p, specs)
+    r = SpectralLibraryReader(p, "0123456789abcdef")
+    by_charge = {}
+    for s in specs:
+        by_charge.setdefault(s["charge"], []).append(s)
+    assert sorted(r.spec_info["charge"]) == sorted(by_charge)
+    for z, group in by_charge.items():
+        info = r.spec_info["charge"][z]
+        assert info["id"].tolist() == [str(s["id"]) for s in group]                    # file order
+        assert info["precursor_mz"].dtype == np.float32
+        assert np.array_equal(info["precursor_mz"], np.array([s["prec_mz"] for s in group], np.float32))
+    s0 = r.read_spectrum(str(specs[3]["id"]))
+    assert s0.identifier == str(specs[3]["id"]) and s0.peptide == specs[3]["peptide"] and not s0.is_processed
+    assert np.array_equal(s0.mz, specs[3]["mz"].astype(np.float32)) and s0.is_decoy == specs[3]["decoy"]
+    assert [x.identifier for x in r.read_all_spectra()] == [str(s["id"]) for s in specs]
+    with r as same:
+        assert same is r and r.get_version() == "null"
+    with pytest.raises(FileNotFoundError):
+        SpectralLibraryReader(str(tmp_path / "nope.splib"))
+    (tmp_path / "lib.sptxt").write_text("Name: X/2\n")
+    with pytest.raises(FileNotFoundError, match="Unrecognized file format"):
+        SpectralLibraryReader(str(tmp_path / "lib.sptxt"))
