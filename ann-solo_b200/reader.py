@@ -11,8 +11,9 @@ The query side: ``read_mgf`` / ``read_query_file`` (reference :868-938) over the
 ``read_mzml`` / ``read_mzxml`` (+ ``_store`` variants) do the same for mzML and mzXML (csrc/mzml_io.cu).
 
 Not mirrored: the ``.spcfg`` / HDF5 cache (reader.py:147-200, :440-556; h5py and joblib stores are
-out of scope, the parsed library stays in host memory), ``.sptxt`` libraries and decoy generation
-(``config.add_decoys``). ``.mgf`` libraries (MassIVE-KB style, SEQ= lines) go through the native MGF parser.
+out of scope, the parsed library stays in host memory) and decoy generation (``config.add_decoys``).
+``.mgf`` libraries (MassIVE-KB style, SEQ= lines) go through the native MGF parser, ``.sptxt`` libraries
+through ``parsers.read_sptxt`` (Python, like the reference's own regex-based reader).
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ import numpy as np
 
 from . import _lib
 from .config import config
-from .parsers import _Annotation, _raise, read_splib
+from .parsers import _Annotation, _raise, read_splib, read_sptxt
 from .spectrum import MsmsSpectrum, process_spectrum
 
 
@@ -42,7 +43,7 @@ def verify_extension(supported_extensions, filename: str) -> None:
 class SpectralLibraryReader:
     """Read spectra from a SpectraST ``.splib`` spectral library (reference reader.py:29-437)."""
 
-    _supported_extensions = [".splib", ".mgf"]
+    _supported_extensions = [".splib", ".sptxt", ".mgf"]   # reference reader.py:34
     is_recreated = False
 
     def __init__(self, filename: str, config_hash: Optional[str] = None, engine=None) -> None:
@@ -52,6 +53,9 @@ class SpectralLibraryReader:
         verify_extension(self._supported_extensions, filename)
         if os.path.splitext(filename)[1].lower() == ".mgf":
             st = _mgf_library_store(filename)                        # reference :283-284 read_mgf as a library
+            self._ids = np.array(st["id"])
+        elif os.path.splitext(filename)[1].lower() == ".sptxt":
+            st = read_sptxt(filename)                                # reference :285-286 read_sptxt
             self._ids = np.array(st["id"])
         else:
             st = read_splib(filename)

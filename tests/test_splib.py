@@ -106,6 +106,58 @@ def test_spectral_library_reader_surface_needs_no_gpu(tmp_path):
         assert same is r and r.get_version() == "null"
     with pytest.raises(FileNotFoundError):
         SpectralLibraryReader(str(tmp_path / "nope.splib"))
-    (tmp_path / "lib.sptxt").write_text("Name: X/2\n")
+    (tmp_path / "lib.msp").write_text("Name: X/2\n")
     with pytest.raises(FileNotFoundError, match="Unrecognized file format"):
-        SpectralLibraryReader(str(tmp_path / "lib.sptxt"))
+        SpectralLibraryReader(str(tmp_path / "lib.msp"))
+
+
+SPTXT = """### a SpectraST text library
+Name: AAAC[160]DEFGK/2
+LibID: 0
+MW: 1012.45
+PrecursorMZ: 506.2321
+Status: Normal
+FullName: K.AAAC[160]DEFGK.L/2 (HCD)
+Comment: AvePrecursorMz=506.5 Mods=1/3,C,Carbamidomethyl Parent=506.232 Remark=_NONE_
+NumPeaks: 5
+201.1234\t1200.5\tb2/0.01\t
+175.1190\t800.0\ty1/-0.00\t
+330.1660\t95.5\ty3-18/0.02,b4^2/0.1\t
+402.2000\t10.0\t?\t
+250.6000\t55.0\ty5^2/0.00\t
+
+Name: PEPTIDER/3
+LibID: 1
+Comment: Parent=319.8231 Mods=0 Spec=Consensus Remark=DECOY_shuffle
+Num Peaks: 3
+100.0\t1.0\tp^3/0.0
+200.0\t2.0\tIWA/0.0
+300.0\t3.0\ta2^2i/0.1
+"""
+
+
+def test_sptxt_library_known_answers(tmp_path):
+    """reference reader.py:324-418 (+ :565-597 annotations, :300-322 ProForma), hand-worked answers."""
+    from ann_solo_b200.parsers import read_sptxt, sptxt_annotation_charge, sptxt_seq_to_proforma
+    from ann_solo_b200.reader import SpectralLibraryReader
+    p = tmp_path / "lib.sptxt"
+    p.write_text(SPTXT)
+    st = read_sptxt(str(p))
+    assert st["id"] == ["1", "2"] and st["prec_z"].tolist() == [2, 3]
+    assert st["prec_mz"].tolist() == [506.2321, 319.8231]                 # PrecursorMZ:, else Parent=
+    assert st["is_decoy"].tolist() == [0, 1] and st["off"].tolist() == [0, 5, 8]
+    # peaks come back m/z-ascending (MsmsSpectrum orders them), annotations follow their peaks
+    assert np.array_equal(st["mz"][:5], np.array([175.1190, 201.1234, 250.6, 330.166, 402.2], np.float32))
+    assert np.array_equal(st["inten"][:5], np.array([800.0, 1200.5, 55.0, 95.5, 10.0], np.float32))
+    assert st["chg"].tolist() == [1, 1, 2, 1, 0, 3, 0, 2]                 # y3-18 -> abs(-1) = 1; '?' and IWA -> none
+    assert st["peptide"] == ["AAAC[160][Carbamidomethyl]DEFGK", "PEPTIDER"]
+    assert [sptxt_annotation_charge(a) for a in ("b2/0.01", "y10-18/0.1", "y5^2/0.0", "p^3/0.0", "a2^2i/0.1", "?", "IWA/0", "")] == \
+        [1, 1, 2, 3, 2, 0, 0, 0]
+    assert sptxt_seq_to_proforma("ACDK", ["0,A,Acetyl", "1,C,Carbamidomethyl"]) == "A[Acetyl]C[Carbamidomethyl]DK"
+    r = SpectralLibraryReader(str(p))
+    assert sorted(r.spec_info["charge"]) == [2, 3] and r.spec_info["charge"][3]["id"].tolist() == ["2"]
+    s = r.read_spectrum("1")
+    assert s.precursor_mz == 506.2321 and [None if a is None else a.charge for a in s.annotation] == [1, 1, 2, 1, None]
+    (tmp_path / "bad.sptxt").write_text("Name: AAK/2\nPrecursorMZ: 300.1\n100.0\t1.0\n")
+    with pytest.raises(ValueError, match="NumPeaks"):
+        read_sptxt(str(tmp_path / "bad.sptxt"))
