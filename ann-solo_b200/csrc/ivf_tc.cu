@@ -637,6 +637,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
             nx.advance();
             const unsigned char *src_n[NR];
             uint32_t nz_n[NR];
+            // row groups (RSTEP rows each) that hold at least one query of this tile
+            const int n_rowgroups = (a.debug & 32) ? NR : (min(tc.cur.G - tc.qb * TC_BM, TC_BM) + RSTEP - 1) / RSTEP;
             if (!(FLAGS & 1)) {  // no prefetch: fetch this tile's rows now
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
@@ -669,9 +671,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                 mbar_wait_prof(smem_u32(&bars->empty_a[stage]), phase ^ 1u, prof_on, pw0);
                 const uint32_t dst0 = a_base + stage * TC_A_BYTES + dst_off;
                 if (!(a.debug & 1)) {
+                    // only the row groups that hold queries of this tile are written: the rows behind the
+                    // group's end keep whatever the stage held (an accumulator row depends on its own A row
+                    // only, and the epilogue never looks at those rows), which saves the gather's LSU slots —
+                    // the resource this kernel is bound by — for short query groups (round 0, tail tiles)
 #pragma unroll
                     for (int i = 0; i < NR; ++i)
-                        cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
+                        if (i < n_rowgroups)
+                            cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
                 }
                 cp_async_arrive_noinc(smem_u32(&bars->full_a[stage]));
                 if (++stage == (uint32_t)n_stages) {
@@ -1210,13 +1217,14 @@ static void tc_prof_report(solo_handle *h, const char *what, int ctas) {
 // stages. The ring is what hides the L2 latency of the query gather, so NB is kept as small as the
 // list lengths allow: the largest multiple of 32 that still leaves at least four stages, but not
 // larger than needed for the longest list (SOLO_TC_NB overrides, for experiments).
-static void tc_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out, int nb_cap = 256) {
+static void tc_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out, int nb_cap = 256, int nb_opt = 0) {
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
     const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64;
     int nb = (avail - 4 * TC_A_BYTES) / (num_kb * 128) / 32 * 32;
     nb = std::min(nb, nb_cap / 32 * 32);
     static const int env_nb = getenv("SOLO_TC_NB") ? atoi(getenv("SOLO_TC_NB")) : 0;
     if (env_nb >= 32 && env_nb <= nb) nb = env_nb / 32 * 32;
+    if (nb_opt >= 32 && nb_opt <= nb) nb = nb_opt / 32 * 32;
     int stages = nb >= 32 ? (avail - num_kb * nb * 128) / TC_A_BYTES : 0;
     *nb_out = nb;
     *stages_out = std::min(stages, TC_MAX_STAGES);
@@ -1249,9 +1257,9 @@ static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, cons
     int nb, stages;
     if (pairs) tc2_smem_plan(ix, &nb, &stages);
     else if (wide) {
-        nb = 256;
+        nb = h->opt_tc_nb >= 32 ? h->opt_tc_nb : 256;
         stages = std::min((TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64) / (TC_A_BYTES + nb * 128), TC_MAX_STAGES);
-    } else tc_smem_plan(ix, &nb, &stages);
+    } else tc_smem_plan(ix, &nb, &stages, 256, h->opt_tc_nb);
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     item_cnt.ensure((size_t)nlist * sizeof(int32_t));
     item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
@@ -1272,7 +1280,7 @@ static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, cons
     a.dim = ix.dim;
     a.nb = nb;
     a.stages = stages;
-    { static const int env_kbb = getenv("SOLO_TC_KBB") ? atoi(getenv("SOLO_TC_KBB")) : 2; a.kbb = env_kbb; }
+    { static const int env_kbb = getenv("SOLO_TC_KBB") ? atoi(getenv("SOLO_TC_KBB")) : 0; a.kbb = env_kbb > 0 ? env_kbb : h->opt_tc_kbb; }
     a.inv_scale = ldexpf(1.f, -(ix.scale_log2 + q_scale_log2));
     a.tau = tau;
     a.buf = buf;

@@ -329,6 +329,12 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_pairs = value != 0;
         } else if (strcmp(key, "front_probes") == 0) {
             h->opt_front_probes = value != 0;
+        } else if (strcmp(key, "tc_nb") == 0) {
+            SOLO_REQUIRE(value >= 0 && value <= 256 && value % 32 == 0, SOLO_EINVAL, "tc_nb must be a multiple of 32 in [0, 256]");
+            h->opt_tc_nb = (int)value;
+        } else if (strcmp(key, "tc_kbb") == 0) {
+            SOLO_REQUIRE(value >= 1 && value <= 6, SOLO_EINVAL, "tc_kbb must be in [1, 6]");
+            h->opt_tc_kbb = (int)value;
         } else {
             SOLO_REQUIRE(false, SOLO_EINVAL, "unknown option '%s'", key);
         }
@@ -850,6 +856,10 @@ int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p) 
             IvfIndex &ix = h->ivf[charge];
             SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
             SOLO_REQUIRE(p->k >= 1 && p->k <= IVF_MAX_K, SOLO_EINVAL, "num_candidates must be in [1, %d]", IVF_MAX_K);
+            // index row i must be library row i (spectral_library.py:443-451): a stale or foreign index would
+            // otherwise address the peak store out of bounds
+            SOLO_REQUIRE(ix.ntotal == L.n, SOLO_ESTATE, "ANN index of charge %d holds %lld rows but the library has %lld",
+                         charge, (long long)ix.ntotal, (long long)L.n);
             // K1: query vectors
             DevBuf &qv = h->scratch[19], &sel = h->scratch[20];
             qv.ensure((size_t)nq * h->hash_len * sizeof(float));
@@ -1367,6 +1377,9 @@ int solo_score_staged_ids(solo_handle *h, int charge, const solo_search_params *
                      "Unknown precursor tolerance mode");
         SOLO_REQUIRE(p->max_pairs > 0 && p->k >= 1, SOLO_EINVAL, "bad parameters");
         SOLO_REQUIRE(q_begin >= 0 && nq_slice >= 0 && q_begin + nq_slice <= nq, SOLO_EINVAL, "query slice out of range");
+        if (h->ivf.count(charge) && h->ivf[charge].nlist > 0)
+            SOLO_REQUIRE(h->ivf[charge].ntotal == L.n, SOLO_ESTATE, "ANN index of charge %d holds %lld rows but the library has %lld",
+                         charge, (long long)h->ivf[charge].ntotal, (long long)L.n);
         if (h->r_nq != nq || h->r_max_pairs != p->max_pairs) ensure_results(h, nq, p->max_pairs);
         if (nq_slice == 0) return;
         DevBuf &ovf = h->r_ovf, &sel = h->scratch[20], &dpos = h->scratch[23];

@@ -187,6 +187,8 @@ struct solo_handle {
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
     int opt_round0_scores = 4096;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
+    int opt_tc_nb = 0;              // > 0: rows of the resident list chunk of the tcgen05 scan (multiple of 32; tuning)
+    int opt_tc_kbb = 2;             // k-blocks per MMA issue batch of the tcgen05 scan (tuning)
     solo::StageProf prof[solo::ST_COUNT];
 
     // vectoriser

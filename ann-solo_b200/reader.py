@@ -40,6 +40,24 @@ def verify_extension(supported_extensions, filename: str) -> None:
         raise FileNotFoundError(f"File {filename} does not exist")
 
 
+def _sort_peaks_by_mz(st: dict) -> None:
+    """Peaks of every spectrum in ascending m/z, intensity and fragment charge attached (stable). The
+    reference gets this from the MsmsSpectrum constructor (spectrum_utils sorts by m/z); K0's range check and
+    K5's merge both assume it, and library files are not guaranteed to be sorted."""
+    mz, off = st["mz"], st["off"]
+    if len(mz) < 2:
+        return
+    inner = np.ones(len(mz), bool)
+    inner[off[1:-1][off[1:-1] < len(mz)]] = False       # first peak of every spectrum starts a new run
+    if not (np.diff(mz) < 0)[inner[1:]].any():
+        return
+    seg = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    order = np.lexsort((mz, seg))
+    for key in ("mz", "inten", "chg"):
+        if key in st:
+            st[key] = np.ascontiguousarray(st[key][order])
+
+
 class SpectralLibraryReader:
     """Read spectra from a SpectraST ``.splib`` spectral library (reference reader.py:29-437)."""
 
@@ -60,6 +78,7 @@ class SpectralLibraryReader:
         else:
             st = read_splib(filename)
             self._ids = np.array([str(i) for i in st["id"]])        # parsers.pyx:145 str(identifier)
+        _sort_peaks_by_mz(st)
         self._store = st
         self._row_of = {ident: r for r, ident in enumerate(self._ids.tolist())}
         self.spec_info = {"charge": {}}

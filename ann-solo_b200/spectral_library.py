@@ -141,7 +141,18 @@ class SpectralLibrary:
                     logging.warning("Missing ANN index for charge %d", charge)
                 else:  # reference _get_ann_index :490 (loaded once: every charge stays resident in HBM)
                     self._engine.ivf_read_index(charge, self._ann_filenames[charge])
-                    self._ann_charges.add(charge)
+                    n_lib = len(self._library_reader.spec_info["charge"][charge]["id"])
+                    n_idx = self._engine.ivf_info(charge)[0]
+                    if n_idx != n_lib:
+                        # a stale or foreign index (library replaced under the same name, index written with
+                        # decoys added, ...): the reference rebuilds on a configuration change (reader.py
+                        # is_recreated); row ids beyond the library must never reach the peak store
+                        logging.warning("ANN index %s holds %d rows but charge %d of the library has %d: rebuilding",
+                                        self._ann_filenames[charge], n_idx, charge, n_lib)
+                        self._engine.ivf_reset(charge)
+                        create_ann_charges.append(charge)
+                    else:
+                        self._ann_charges.add(charge)
             self._create_ann_indexes(create_ann_charges, centroids or {}, train_iters)
 
     def _get_hyperparameter_hash(self) -> str:

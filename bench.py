@@ -301,7 +301,8 @@ def run_solo(args, wl, rank, world, local_rank):
     stages = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
 
     # the CPU baseline is reported by the single-GPU run only (torchrun also pins OMP_NUM_THREADS=1)
-    cpu = cpu_baseline(wl, per_charge, q_by_charge, eng) if (not args.no_cpu_baseline and world == 1) else None
+    cpu, parity = (cpu_baseline(wl, per_charge, q_by_charge, eng, host_out)
+                   if (not args.no_cpu_baseline and world == 1) else (None, None))
     extras = measure_extras(eng, charges, q_by_charge, nq_rank, torch) if args.extras else None
     line = {
         "metric": "query spectra/sec, cascade open search", "value": round(value, 1), "unit": "spectra/s",
@@ -314,11 +315,14 @@ def run_solo(args, wl, rank, world, local_rank):
         "e2e": {"value": round(e2e, 1), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stages,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity": parity,
     }
     if extras:
         line["extras"] = extras
     _emit(json.dumps(line))
+    if parity and parity["mismatch"]:
+        log(f"PARITY FAILURE: {parity['mismatch']} of {parity['checked']} sampled queries differ from the CPU reference path")
+        sys.exit(1)
 
 
 def measure_extras(eng, charges, q_by_charge, nq_rank, torch):
@@ -436,27 +440,55 @@ def run_sharded(args, wl, rank, world, eng, charges, q_by_charge, params, torch,
     }))
 
 
-def cpu_pipeline(o, store, q, cent, assign, nlist, wl, charge, threads, use_ref):
+def cpu_pipeline(o, store, q, cent, assign, nlist, wl, charge, threads, use_ref, simd=True):
     """The reference's CPU path for one batch of one charge: vectorise, IVF-Flat search (dense
     SIMD scan like Faiss), post-top-k window mask, SpectrumMatcher::dot (the reference's own
     compiled core when oracle/_ref exists)."""
     qv = o.vectorize(q["mz"], q["inten"], q["off"])
     _, ann = o.ivf_search(qv, cent, store["_list_off"], store["_list_ids"], store["_list_vecs"],
-                          min(wl["nprobe"], nlist), wl["k"], simd=True, n_threads=threads)
+                          min(wl["nprobe"], nlist), wl["k"], simd=simd, n_threads=threads)
     cand, coff = o.candidates(q["prec_mz"], store["prec_mz"].astype(np.float32), store["valid"], charge, OPEN_TOL,
                               OPEN_MODE, ann)
     if use_ref:
-        return o.ref_best_match_batch(q, store, cand, coff, FRAG_TOL, True, n_threads=threads)
-    return o.best_match_batch(q, store, cand, coff, FRAG_TOL, True, sort_mode=0, n_threads=threads)
+        bp, bs, npairs, pairs = o.ref_best_match_batch(q, store, cand, coff, FRAG_TOL, True, n_threads=threads)
+    else:
+        bp, bs, npairs, pairs = o.best_match_batch(q, store, cand, coff, FRAG_TOL, True, sort_mode=0, n_threads=threads)
+    row = np.full(len(bp), -1, np.int32)
+    has = bp >= 0
+    row[has] = cand[coff[:-1][has] + bp[has]]
+    return {"best_row": row, "score": bs, "n_pairs": npairs, "pairs": pairs, "n_cand": np.diff(coff).astype(np.int32)}
 
 
-def cpu_baseline(wl, per_charge, q_by_charge, eng):
-    """Bounded sample of the same workload on the host cores, same centroids/lists as the GPU."""
+def parity_mismatches(cpu, gpu, n):
+    """Queries (of the first n) whose GPU result differs from the CPU reference path's: library row of the
+    best match, score bits, candidate count, number of matched peak pairs and the pair set itself
+    (canonically sorted: std::sort leaves the order inside exact product ties unspecified)."""
+    bad = []
+    for i in range(n):
+        ok = (cpu["best_row"][i] == gpu["best_row"][i] and cpu["n_cand"][i] == gpu["n_cand"][i])
+        if ok and cpu["best_row"][i] >= 0:
+            m = int(cpu["n_pairs"][i])
+            ok = (m == int(gpu["n_pairs"][i]) and
+                  np.float64(cpu["score"][i]).view(np.uint64) == np.float64(gpu["score"][i]).view(np.uint64))
+            if ok and m:
+                a = np.asarray(cpu["pairs"][i, :m], np.int64)
+                b = np.asarray(gpu["pairs"][i, :m], np.int64)
+                ok = np.array_equal(a[np.lexsort((a[:, 1], a[:, 0]))], b[np.lexsort((b[:, 1], b[:, 0]))])
+        if not ok:
+            bad.append(i)
+    return bad
+
+
+def cpu_baseline(wl, per_charge, q_by_charge, eng, gpu_out=None):
+    """Bounded sample of the same workload on the host cores, same centroids/lists as the GPU. When the
+    GPU results of the same batch are given (`gpu_out[z]`, the e2e leg's host buffers), the sampled queries
+    are compared with them: returns (cpu_baseline object, parity object)."""
     from ann_solo_b200 import synth
     from oracle import solo_oracle as o  # cpu_baseline leg only
     threads = o.num_threads()
     use_ref = o.have_ref()
     total_q, total_s = 0, 0.0
+    checked = mismatch = resolved = 0
     n_all = sum(len(q["prec_mz"]) for q in q_by_charge.values())
     for z, q in q_by_charge.items():
         take = max(8, int(round(wl["cpu_sample"] * len(q["prec_mz"]) / n_all)))
@@ -468,15 +500,35 @@ def cpu_baseline(wl, per_charge, q_by_charge, eng):
         store["_list_off"], store["_list_ids"], store["_list_vecs"] = o.build_lists(x, assign, len(cent))
         del x
         t0 = time.perf_counter()
-        cpu_pipeline(o, store, qs, cent, assign, len(cent), wl, z, threads, use_ref)
+        res = cpu_pipeline(o, store, qs, cent, assign, len(cent), wl, z, threads, use_ref)
         total_s += time.perf_counter() - t0
         total_q += len(qs["prec_mz"])
+        if gpu_out is not None:
+            bad = parity_mismatches(res, gpu_out[z], len(qs["prec_mz"]))
+            n_simd = len(bad)
+            if bad:
+                # the timed CPU scan sums in SIMD partial sums (like Faiss' fvec_inner_product), which can flip
+                # the order of two near-equal scores at the k-th boundary; the parity definition is the
+                # sequential-fmaf oracle, so these queries are looked at again with it
+                sub = synth.take_spectra(qs, np.asarray(bad))
+                again = cpu_pipeline(o, store, sub, cent, assign, len(cent), wl, z, threads, use_ref, simd=False)
+                gsub = {k_: gpu_out[z][k_][np.asarray(bad)] for k_ in ("best_row", "score", "n_pairs", "pairs", "n_cand")}
+                bad = parity_mismatches(again, gsub, len(bad))
+            checked += len(qs["prec_mz"])
+            mismatch += len(bad)
+            resolved += n_simd - len(bad)
+            log(f"parity z={z}: {len(qs['prec_mz'])} sampled queries vs the GPU results of the same batch: "
+                f"{len(bad)} mismatches ({n_simd} before the sequential-fmaf re-check)")
         del store
+    parity = None if gpu_out is None else {
+        "checked": int(checked), "mismatch": int(mismatch), "simd_order_rechecked": int(resolved),
+        "fields": "best library row, score bits (f64), candidate count, matched-pair count, canonical pair set",
+        "against": "reference SpectrumMatch.cpp (oracle/_ref)" if use_ref else "ported scorer (oracle)"}
     return {"value": round(total_q / total_s, 2), "unit": "spectra/s", "cores": threads,
             "kind": "reference" if use_ref else "port",
             "sample": f"{total_q} queries of the same workload (all charges), vectorise + restated Faiss IVF-Flat "
                       f"(dense SIMD scan, OpenMP) + window + {'reference SpectrumMatch.cpp' if use_ref else 'ported scorer'}"
-                      f" on {threads} threads, {total_s:.1f}s"}
+                      f" on {threads} threads, {total_s:.1f}s"}, parity
 
 
 def run_reference(args, wl, rank, world):
