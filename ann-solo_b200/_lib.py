@@ -33,7 +33,8 @@ class SearchParams(C.Structure):
 class ProcessParams(C.Structure):
     _fields_ = [("min_mz", C.c_double), ("max_mz", C.c_double), ("min_mz_range", C.c_double),
                 ("remove_precursor_tolerance", C.c_double), ("min_intensity", C.c_double), ("min_peaks", C.c_int32),
-                ("max_peaks", C.c_int32), ("remove_precursor", C.c_int32), ("scaling", C.c_int32)]
+                ("max_peaks", C.c_int32), ("remove_precursor", C.c_int32), ("scaling", C.c_int32),
+                ("resolution", C.c_int32), ("reserved", C.c_int32)]
 
 
 SCALING = {None: 0, "root": 1, "sqrt": 1, "rank": 2}

@@ -13,7 +13,10 @@
 //     max_peaks largest under (intensity, peak index) — a stable ascending argsort's tail;
 //   * rank scaling gives max_peaks - (number of kept peaks greater under the same order);
 //   * the norm is float32(sqrt(sum of float64 squares)) with NumPy's pairwise summation order.
-// `resolution` (round + merge) is not implemented on the device (SOLO_EINVAL).
+//   * round(resolution, 'sum') (spectrum.py:84-89): NumPy's round — rint(x * 10^d) / 10^d in the m/z array's
+//     precision —, peaks that land on the same value (adjacent, m/z is ascending) are merged: float32 sum
+//     in peak order, the merged peak stands where the group's most intense member (first on ties) stood, so
+//     that its annotation / fragment charge follows it.
 #include "solo_common.cuh"
 
 namespace solo {
@@ -39,6 +42,10 @@ __device__ double numpy_pairwise_sum(const double *a, int n) {
     for (; i < n; ++i) s = __dadd_rn(s, a[i]);
     return s;
 }
+
+// np.round(x, d), d >= 0: rint(x * 10^d) / 10^d in the array's precision (PyArray_Round)
+__device__ __forceinline__ float round_decimals(float x, float f) { return __fdiv_rn(rintf(__fmul_rn(x, f)), f); }
+__device__ __forceinline__ double round_decimals(double x, double f) { return __ddiv_rn(rint(__dmul_rn(x, f)), f); }
 
 template <typename T>
 __global__ void __launch_bounds__(K0_THREADS)
@@ -66,6 +73,15 @@ k0_process_kernel(const ProcessArgs a) {
         return;
     }
     const T lo = (T)P.min_mz, hi = (T)P.max_mz, min_range = (T)P.min_mz_range;
+    const bool do_round = P.resolution >= 0;
+    T rf = (T)1;
+    if (do_round) {
+        double f = 1.0;
+        for (int d = 0; d < P.resolution; ++d) f *= 10.0;   // exact for d <= 22
+        rf = (T)f;
+    }
+    // m/z of raw peak i as every step after set_mz_range sees it
+    auto MZ = [&](int i) -> T { return do_round ? round_decimals(mz[i], rf) : mz[i]; };
 
     // count / first / last of the peaks currently kept; every thread returns the same verdict
     auto valid_now = [&]() -> bool {
@@ -101,7 +117,7 @@ k0_process_kernel(const ProcessArgs a) {
         }
         __syncthreads();
         if (s_count < P.min_peaks || s_count == 0) return false;
-        return (T)(mz[s_last] - mz[s_first]) >= min_range;   // spectrum.py:14-36, in the array's precision
+        return (T)(MZ(s_last) - MZ(s_first)) >= min_range;   // spectrum.py:14-36, in the array's precision
     };
 
     // set_mz_range (spectrum.py:79)
@@ -111,6 +127,33 @@ k0_process_kernel(const ProcessArgs a) {
     }
     __syncthreads();
     if (!valid_now()) return;
+    // round(resolution, 'sum') (spectrum.py:84-89): the kept peaks are the contiguous index range
+    // [s_first, s_last] (m/z ascending); the thread of a group's first peak merges the group
+    if (do_round) {
+        const int f0 = s_first, l0 = s_last;
+        __syncthreads();
+        for (int i = f0 + tid; i <= l0; i += K0_THREADS) {
+            const T r = MZ(i);
+            if (i > f0 && MZ(i - 1) == r) continue;
+            float sum = s_int[i], top = s_int[i];   // np.add.at on zeros: 0 + x is x
+            int best = i, e = i + 1;
+            while (e <= l0 && MZ(e) == r) {
+                sum = __fadd_rn(sum, s_int[e]);
+                if (s_int[e] > top) {
+                    top = s_int[e];
+                    best = e;
+                }
+                ++e;
+            }
+            if (e > i + 1) {
+                for (int j = i; j < e; ++j) s_keep[j] = 0;
+                s_keep[best] = 1;
+                s_int[best] = sum;
+            }
+        }
+        __syncthreads();
+        if (!valid_now()) return;
+    }
     // remove_precursor_peak(tol, 'Da', isotope = 2) (spectrum.py:90-96)
     if (P.remove_precursor) {
         const int z = a.prec_charge[sp];
@@ -120,7 +163,7 @@ k0_process_kernel(const ProcessArgs a) {
             for (int iso = 0; iso < 3; ++iso) {
                 const T target = (T)__dadd_rn(__ddiv_rn(__dadd_rn(neutral, (double)iso), (double)c), 1.0072766);
                 for (int i = tid; i < n; i += K0_THREADS) {
-                    T d = mz[i] - target;
+                    T d = MZ(i) - target;
                     if (d < 0) d = -d;
                     if (s_keep[i] && d <= tol) s_keep[i] = 0;
                 }
@@ -184,7 +227,7 @@ k0_process_kernel(const ProcessArgs a) {
             float v = s_int[i];
             if (P.scaling == SOLO_SCALING_ROOT) v = __fsqrt_rn(v);
             else if (P.scaling == SOLO_SCALING_RANK) v = (float)(P.max_peaks - ((int)s_keep[i] - 1));
-            o_mz[pos] = mz[i];
+            o_mz[pos] = MZ(i);
             o_int[pos] = v;
             o_idx[pos] = i;
             s_sq[pos] = __dmul_rn((double)v, (double)v);

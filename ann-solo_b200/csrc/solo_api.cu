@@ -1047,6 +1047,7 @@ int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const fl
                      "Unknown intensity scaling");
         SOLO_REQUIRE(!p->remove_precursor || (prec_mz && prec_charge), SOLO_EINVAL,
                      "remove_precursor needs precursor m/z and charge");
+        SOLO_REQUIRE(p->resolution >= -1 && p->resolution <= 12, SOLO_EINVAL, "resolution must be -1 (none) or 0..12 decimals");
         SOLO_REQUIRE(n < (int64_t)0x7fffffff && offsets[0] == 0, SOLO_EINVAL, "bad offsets");
         const int64_t npk = offsets[n];
         const size_t esz = mz_is_f64 ? 8 : 4;

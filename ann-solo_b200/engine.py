@@ -287,8 +287,8 @@ class SoloEngine:
         store in one launch. Returns a processed peak store (``valid`` = is_valid; invalid spectra
         keep no peaks) plus ``src`` = index of every kept peak inside its raw spectrum; peak charges
         (``chg``) and float64 m/z follow the kept peaks."""
-        if resolution is not None:
-            raise ValueError("resolution (round + merge) is not implemented on the device")
+        if resolution is not None and not 0 <= int(resolution) <= 12:
+            raise ValueError("resolution must be a number of decimals in [0, 12]")
         if scaling not in _lib.SCALING:
             raise ValueError("Unknown intensity scaling")
         is64 = mz_vec is not None and mz_vec.dtype == np.float64
@@ -300,7 +300,7 @@ class SoloEngine:
         pz = _c(store["prec_z"], np.int32) if store.get("prec_z") is not None else None
         prm = _lib.ProcessParams(float(min_mz), float(max_mz), float(min_mz_range), float(remove_precursor_tolerance),
                                  float(min_intensity), int(min_peaks), int(max_peaks), int(bool(remove_precursor)),
-                                 _lib.SCALING[scaling])
+                                 _lib.SCALING[scaling], -1 if resolution is None else int(resolution), 0)
         o_mz = np.empty((n, max_peaks), mz.dtype)
         o_in = np.empty((n, max_peaks), np.float32)
         o_ix = np.empty((n, max_peaks), np.int32)
@@ -314,6 +314,7 @@ class SoloEngine:
         np.cumsum(o_ct, out=new_off[1:])
         src = o_ix[keep]
         gsrc = np.repeat(off[:-1], o_ct) + src
+        # (with `resolution` a merged peak stands at its group's most intense member: src / chg follow that one)
         out = dict(mz=o_mz[keep].astype(np.float32), inten=o_in[keep], off=new_off, valid=o_va, src=src,
                    prec_mz=store.get("prec_mz"), prec_z=store.get("prec_z"))
         if is64:

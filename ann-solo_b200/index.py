@@ -22,7 +22,11 @@ class IndexFlatIP:
         self.d = d
 
 
-class IndexIVFFlat:
+class IndexIVF:
+    """Base name the reference annotates with (spectral_library.py:457)."""
+
+
+class IndexIVFFlat(IndexIVF):
     """reference spectral_library.py:167-181, :443-444, :497."""
 
     def __init__(self, quantizer, d: int, nlist: int, metric=METRIC_INNER_PRODUCT, engine=None, slot=None):
@@ -67,6 +71,26 @@ class IndexIVFFlat:
 
     def reconstruct_n(self, i0: int = 0, ni: int = None) -> np.ndarray:
         return self._eng.ivf_reconstruct(self._slot, i0, ni)
+
+
+def get_num_gpus() -> int:
+    """faiss.get_num_gpus (reference spectral_library.py:71). Answers 0 on purpose: every index of this module
+    already lives on the device, so the reference takes its plain branch (`index.nprobe = n`, :497) instead of
+    cloning to a GpuIndex and clamping num_probe / num_candidates to Faiss-GPU's 1024 (:76-86)."""
+    return 0
+
+
+class StandardGpuResources:   # accepted for callers that force the reference's GPU branch; nothing to hold
+    pass
+
+
+class GpuClonerOptions:
+    useFloat16 = False
+
+
+def index_cpu_to_gpu(res, device: int, index: "IndexIVFFlat", options=None) -> "IndexIVFFlat":
+    """faiss.index_cpu_to_gpu (reference spectral_library.py:494): the index is on the device already."""
+    return index
 
 
 def write_index(index: IndexIVFFlat, fname: str) -> None:

@@ -70,6 +70,107 @@ def _select(spectrum, keep):
         spectrum._annotation = [ann[i] for i in idx]
 
 
+# The five spectrum_utils (<0.4) peak operations the reference's process_spectrum calls (spectrum.py:78-107), as
+# methods with spectrum_utils' names and argument order, each changing the spectrum in place and returning it.
+# spectrum_utils is absent here: the bodies are restated from its documented behaviour and are
+# what oracle/solo_oracle.py:process_spectrum_np and the K0 kernel compute bit for bit.
+def _set_mz_range(self, min_mz, max_mz):
+    _select(self, (self._mz >= min_mz) & (self._mz <= max_mz))
+    return self
+
+
+def _round(self, decimals: int = 0, combine: str = "sum"):
+    """Round m/z to `decimals` and merge peaks that fall on the same value: intensities are combined ('sum' or
+    'max'), the annotation of the most intense peak of the group is kept (first one on ties)."""
+    if len(self._mz) == 0:
+        return self
+    r = np.round(self._mz, decimals)
+    head = np.ones(len(r), bool)
+    head[1:] = r[1:] != r[:-1]          # m/z is ascending: equal rounded values are adjacent
+    group = np.cumsum(head) - 1
+    n = int(group[-1]) + 1
+    if n < len(r):
+        if combine == "sum":
+            merged = np.zeros(n, np.float32)
+            np.add.at(merged, group, self._intensity)     # float32, in peak order
+        elif combine == "max":
+            merged = np.full(n, -np.inf, np.float32)
+            np.maximum.at(merged, group, self._intensity)
+        else:
+            raise ValueError("Unknown method to combine peak intensities")
+        ann = self._annotation
+        if ann is not None:
+            best = np.zeros(n, np.int64)
+            top = np.full(n, -np.inf)
+            for i, g in enumerate(group):                   # first most intense peak of each group
+                if self._intensity[i] > top[g]:
+                    top[g], best[g] = self._intensity[i], i
+            self._annotation = [ann[i] for i in best]
+        self._mz, self._intensity = r[head], merged
+    else:
+        self._mz = r
+    return self
+
+
+def _remove_precursor_peak(self, fragment_tol_mass, fragment_tol_mode, isotope: int = 0):
+    z = self.precursor_charge
+    neutral = (self.precursor_mz - 1.0072766) * z
+    rm = np.zeros(len(self._mz), bool)
+    for c in range(z, 0, -1):
+        for iso in range(isotope + 1):
+            target = (neutral + iso) / c + 1.0072766
+            if fragment_tol_mode == "Da":
+                rm |= np.abs(self._mz - target) <= fragment_tol_mass
+            elif fragment_tol_mode == "ppm":
+                rm |= np.abs(self._mz - target) / target * 1e6 <= fragment_tol_mass
+            else:
+                raise ValueError("Unknown fragment tolerance mode")
+    _select(self, ~rm)
+    return self
+
+
+def _filter_intensity(self, min_intensity: float = 0.0, max_num_peaks=None):
+    inten = self._intensity
+    if max_num_peaks is None:
+        max_num_peaks = len(inten)
+    order = np.argsort(inten, kind="stable")
+    thr = min_intensity * (inten[order[-1]] if len(order) else 0.0)
+    start = int(np.searchsorted(inten[order], thr, side="right"))
+    sel = order[max(start, len(order) - max_num_peaks):]
+    keep = np.zeros(len(inten), bool)
+    keep[sel] = True
+    _select(self, keep)
+    return self
+
+
+def _scale_intensity(self, scaling=None, max_intensity=None, degree: int = 2, base: int = 2, max_rank=None):
+    if scaling == "root":
+        self._intensity = np.power(self._intensity, 1 / degree).astype(np.float32) if degree != 2 else \
+            np.sqrt(self._intensity).astype(np.float32)
+    elif scaling == "log":
+        self._intensity = (np.log1p(self._intensity) / np.log(base)).astype(np.float32)
+    elif scaling == "rank":
+        if max_rank is None:
+            max_rank = len(self._intensity)
+        if max_rank < len(self._intensity):
+            raise ValueError("`max_rank` should be greater than or equal to the number of peaks in the spectrum")
+        inten = self._intensity
+        self._intensity = (max_rank - np.argsort(np.argsort(inten, kind="stable")[::-1], kind="stable")
+                           ).astype(np.float32)
+    elif scaling is not None:
+        raise ValueError("Unknown intensity scaling")
+    if max_intensity is not None:
+        self._intensity = (self._intensity * max_intensity / self._intensity.max()).astype(np.float32)
+    return self
+
+
+MsmsSpectrum.set_mz_range = _set_mz_range
+MsmsSpectrum.round = _round
+MsmsSpectrum.remove_precursor_peak = _remove_precursor_peak
+MsmsSpectrum.filter_intensity = _filter_intensity
+MsmsSpectrum.scale_intensity = _scale_intensity
+
+
 def process_spectrum(spectrum, is_library: bool):
     """Reference spectrum.py:57-119, same order of operations and validity checks."""
     if spectrum.is_processed:
@@ -81,52 +182,26 @@ def process_spectrum(spectrum, is_library: bool):
         spectrum.is_processed = True
         return spectrum
 
-    _select(spectrum, (spectrum._mz >= config.min_mz) & (spectrum._mz <= config.max_mz))  # set_mz_range
+    spectrum.set_mz_range(config.min_mz, config.max_mz)
     if not _check_spectrum_valid(spectrum._mz, min_peaks, min_mz_range):
         return invalid()
-    if config.resolution is not None:  # round(decimals, 'sum')
-        r = np.round(spectrum._mz, config.resolution)
-        uniq, first, inv = np.unique(r, return_index=True, return_inverse=True)
-        summed = np.zeros(len(uniq), np.float32)
-        np.add.at(summed, inv, spectrum._intensity)
-        ann = spectrum._annotation
-        spectrum._mz, spectrum._intensity = uniq.astype(spectrum._mz.dtype), summed
-        if ann is not None:
-            spectrum._annotation = [ann[i] for i in first]
+    if config.resolution is not None:
+        spectrum.round(config.resolution, "sum")
         if not _check_spectrum_valid(spectrum._mz, min_peaks, min_mz_range):
             return invalid()
-    if config.remove_precursor:  # remove_precursor_peak(tol, 'Da', 2)
-        z = spectrum.precursor_charge
-        neutral = (spectrum.precursor_mz - 1.0072766) * z
-        rm = np.zeros(len(spectrum._mz), bool)
-        for c in range(z, 0, -1):
-            for iso in range(3):
-                rm |= np.abs(spectrum._mz - ((neutral + iso) / c + 1.0072766)) <= config.remove_precursor_tolerance
-        _select(spectrum, ~rm)
+    if config.remove_precursor:
+        spectrum.remove_precursor_peak(config.remove_precursor_tolerance, "Da", 2)
         if not _check_spectrum_valid(spectrum._mz, min_peaks, min_mz_range):
             return invalid()
     max_peaks = config.max_peaks_used_library if is_library else config.max_peaks_used
-    inten = spectrum._intensity  # filter_intensity(min_intensity, max_num_peaks)
-    order = np.argsort(inten, kind="stable")
-    thr = config.min_intensity * (inten[order[-1]] if len(order) else 0.0)
-    start = int(np.searchsorted(inten[order], thr, side="right"))
-    sel = order[max(start, len(order) - max_peaks):]
-    keep = np.zeros(len(inten), bool)
-    keep[sel] = True
-    _select(spectrum, keep)
+    spectrum.filter_intensity(config.min_intensity, max_peaks)
     if not _check_spectrum_valid(spectrum._mz, min_peaks, min_mz_range):
         return invalid()
     scaling = config.scaling
     if scaling == "sqrt":
         scaling = "root"
-    if scaling == "root":
-        spectrum._intensity = np.sqrt(spectrum._intensity).astype(np.float32)
-    elif scaling == "rank":
-        inten = spectrum._intensity
-        spectrum._intensity = (max_peaks - np.argsort(np.argsort(inten, kind="stable")[::-1], kind="stable")
-                               ).astype(np.float32)
-    elif scaling is not None:
-        raise ValueError("Unknown intensity scaling")
+    if scaling is not None:
+        spectrum.scale_intensity(scaling, max_rank=max_peaks)
     nrm = np.float32(np.sqrt(np.sum(spectrum._intensity.astype(np.float64) ** 2)))
     spectrum._intensity = (spectrum._intensity / nrm).astype(np.float32)  # _norm_intensity, spectrum.py:39-54
     spectrum.is_valid = True

@@ -200,7 +200,7 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
  * batch of raw spectra (m/z ascending): set_mz_range, validity (:14-36, re-checked after every step),
  * remove_precursor_peak(tol, 'Da', 2), filter_intensity(min_intensity, max_peaks),
  * scale_intensity('root' | 'rank', max_rank = max_peaks), L2 norm. The config keys are the reference's
- * (config.py:71-117); `resolution` must be None (not implemented on the device). Outputs are
+ * (config.py:71-117); `resolution` = decimals of spectrum.round(d, 'sum') (spectrum.py:84-89) or -1. Outputs are
  * fixed-stride rows of max_peaks entries: out_mz (same type as mz), out_intensity, out_index (position
  * of the kept peak in its raw spectrum — carries annotations/peak charges along), out_count (0 for an
  * invalid spectrum), out_valid (is_valid). */
@@ -214,6 +214,8 @@ typedef struct solo_process_params {
     int32_t max_peaks;                     /* config.max_peaks_used(_library), <= 128 */
     int32_t remove_precursor;              /* config.remove_precursor */
     int32_t scaling;                       /* config.scaling: SOLO_SCALING_* ('sqrt' == root) */
+    int32_t resolution;                    /* config.resolution: decimals of round(d, 'sum') (0..12), -1 = None */
+    int32_t reserved;
 } solo_process_params;
 int solo_process_spectra(solo_handle *h, const void *mz, int mz_is_f64, const float *intensity,
                          const int64_t *offsets, const double *prec_mz, const int32_t *prec_charge, int64_t n,

@@ -292,15 +292,17 @@ def process_spectrum_np(mz, intensity, precursor_mz, precursor_charge, *, min_mz
     mz, intensity, idx = mz[keep], intensity[keep], idx[keep]
     if not valid(mz):
         return mz, intensity, False, idx
-    if resolution is not None:  # round(decimals, 'sum')
+    if resolution is not None:  # round(decimals, 'sum'): NumPy's round in the array's precision, equal values merged
         r = np.round(mz, resolution)
         uniq, inv = np.unique(r, return_inverse=True)
         summed = np.zeros(len(uniq), np.float32)
-        np.add.at(summed, inv, intensity)
-        first = np.full(len(uniq), -1)
-        for i in range(len(r) - 1, -1, -1):
-            first[inv[i]] = idx[i]
-        mz, intensity, idx = uniq.astype(mz.dtype), summed, first
+        np.add.at(summed, inv, intensity)          # float32, in peak order
+        rep = np.full(len(uniq), -1)
+        top = np.full(len(uniq), -np.inf)
+        for i in range(len(r)):                     # the group's most intense peak (first on ties) carries the annotation
+            if intensity[i] > top[inv[i]]:
+                top[inv[i]], rep[inv[i]] = intensity[i], idx[i]
+        mz, intensity, idx = uniq.astype(mz.dtype), summed, rep
         if not valid(mz):
             return mz, intensity, False, idx
     if remove_precursor:  # remove_precursor_peak(tol, 'Da', isotope=2)

@@ -81,6 +81,11 @@ def load_reference(faiss_mod, spectrum_match_mod, reader_mod, utils_mod, spectru
                 k.pop(key, None)
             super().__init__()
 
+        def parse_args(self, args=None, namespace=None):   # configargparse also takes one string
+            if isinstance(args, str):
+                args = args.split()
+            return super().parse_args(args, namespace)
+
     cap.ArgParser = ArgParser
     cap.ArgumentDefaultsHelpFormatter = argparse.ArgumentDefaultsHelpFormatter
     sys.modules["configargparse"] = cap

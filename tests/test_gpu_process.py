@@ -36,6 +36,10 @@ CONFIGS = [
     dict(remove_precursor=True, remove_precursor_tolerance=0.05),
     dict(remove_precursor=True, remove_precursor_tolerance=1.5, scaling="sqrt", min_intensity=0.05, max_peaks=128),
     dict(min_mz=101.5, max_mz=1500.25, min_peaks=20, min_mz_range=400.5, max_peaks=50),
+    # round(resolution, 'sum') (reference spectrum.py:84-89): whole-number m/z merges many peaks, 1 and 2 decimals few
+    dict(resolution=0),
+    dict(resolution=1, remove_precursor=True, remove_precursor_tolerance=0.5, scaling="root"),
+    dict(resolution=2, scaling=None, max_peaks=64, min_intensity=0.02),
 ]
 
 
@@ -78,7 +82,7 @@ def test_processed_spectra_are_fixed_points_and_errors(engine, oracle):
         m = once["mz"][once["off"][i]:once["off"][i + 1]]
         assert 10 <= len(m) <= 50 and (np.diff(m) >= 0).all() and m[0] >= 11 and m[-1] <= 2010
     with pytest.raises(ValueError, match="resolution"):
-        engine.process_spectra(store, resolution=2)
+        engine.process_spectra(store, resolution=13)
     with pytest.raises(ValueError, match="scaling"):
         engine.process_spectra(store, scaling="log")
     from ann_solo_b200 import SoloError

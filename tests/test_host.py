@@ -84,6 +84,40 @@ def test_process_spectrum_matches_oracle_restatement(oracle, scaling):
         config.update(dict(scaling="rank", remove_precursor=False, remove_precursor_tolerance=0))
 
 
+@pytest.mark.parametrize("resolution", [0, 1, 2])
+def test_process_spectrum_with_resolution(oracle, resolution):
+    """round(resolution, 'sum') (reference spectrum.py:84-89): the host method equals the oracle restatement, the
+    merged peak keeps the annotation of its group's most intense member."""
+    from ann_solo_b200.config import config
+    from ann_solo_b200.spectrum import MsmsSpectrum, process_spectrum
+    rng = np.random.default_rng(9 + resolution)
+    config.update(dict(resolution=resolution))
+    try:
+        n_valid = 0
+        for i in range(40):
+            n = int(rng.integers(50, 600))
+            mz = np.sort(rng.uniform(5.0, 2100.0, n))
+            if i % 2:
+                mz = mz.astype(np.float32)
+            inten = rng.exponential(1.0, n).astype(np.float32)
+            ann = list(range(n))
+            s = process_spectrum(MsmsSpectrum(i, 600.0, 2, mz.copy(), inten.copy(), annotation=ann), is_library=True)
+            omz, oint, ovalid, oidx = oracle.process_spectrum_np(mz, inten, 600.0, 2, resolution=resolution)
+            assert s.is_valid == ovalid
+            if ovalid:
+                n_valid += 1
+                assert np.array_equal(s.mz, omz) and np.array_equal(s.intensity, oint)
+                assert s.annotation == list(oidx)
+        assert n_valid > 20
+    finally:
+        config.update(dict(resolution=None))
+    sp = MsmsSpectrum(0, 500.0, 2, np.array([100.01, 100.04, 100.2, 250.0]), np.array([1.0, 3.0, 2.0, 5.0], np.float32),
+                      annotation=["a", "b", "c", "d"])
+    sp.round(1, "sum")
+    assert np.array_equal(sp.mz, [100.0, 100.2, 250.0]) and np.array_equal(sp.intensity, [4.0, 2.0, 5.0])
+    assert sp.annotation == ["b", "c", "d"]
+
+
 def test_rank_scaling_is_what_synth_generates(synth):
     lib = synth.make_library(200, seed=3)
     for r in range(0, 200, 17):
