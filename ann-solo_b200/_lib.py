@@ -86,6 +86,9 @@ SYMBOLS = {
     "solo_fetch_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "solo_search_batch": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "solo_stage_queries_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "solo_fetch_results_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "solo_wait_results": (C.c_int, [_vp, C.c_int]),
     "solo_process_spectra": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "solo_splib_count": (C.c_int, [C.c_char_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.c_char_p, C.c_int]),
     "solo_splib_read": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -104,6 +107,8 @@ SYMBOLS = {
     "solo_ssm_features_staged": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "solo_ivf_set_owned_lists": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "solo_ivf_search_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "solo_ivf_probe_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "solo_ivf_scan_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "solo_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "solo_score_staged_ids": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, C.c_int, C.c_int]),
     "solo_profile_enable": (C.c_int, [_vp, C.c_int]),

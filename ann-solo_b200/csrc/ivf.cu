@@ -1312,65 +1312,70 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         tc_prepare_queries(h, ix, a.q, nq, q_scale_log2, qh.as<__half>(), qmask.as<uint32_t>());
     }
 
-    DevBuf &coarse = h->scratch[7];
-    const int pitch = (nlist + 31) & ~31;
-    coarse.ensure((size_t)nq * pitch * sizeof(float));
-    {
-        StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
-        if (use_tc_coarse)
-            launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, coarse.as<float>(), pitch);
-        else
-            launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
-                             coarse.as<float>(), nullptr, pitch);
-    }
     DevBuf &probes = h->scratch[8], &pkeys = h->scratch[9];
-    probes.ensure((size_t)nq * nprobe * sizeof(int32_t));
-    int32_t *d_probes = probes.as<int32_t>();
-    {
-        StageTimer t(h, ST_PROBE_SELECT, 1 + (a.sort_probes ? 1 : 0));
-        size_t smem = (size_t)nlist * sizeof(uint32_t);
-        SOLO_CUDA(cudaFuncSetAttribute(select_probes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned long long *d_keys = nullptr;
-        if (a.sort_probes) {
-            pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
-            d_keys = pkeys.as<unsigned long long>();
+    const int32_t *d_probes_c = a.given_probes;
+    if (!a.given_probes) {
+        probes.ensure((size_t)nq * nprobe * sizeof(int32_t));
+        int32_t *d_probes = probes.as<int32_t>();
+        d_probes_c = d_probes;
+        DevBuf &coarse = h->scratch[7];
+        const int pitch = (nlist + 31) & ~31;
+        coarse.ensure((size_t)nq * pitch * sizeof(float));
+        {
+            StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
+            if (use_tc_coarse)
+                launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, coarse.as<float>(), pitch);
+            else
+                launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
+                                 coarse.as<float>(), nullptr, pitch);
         }
-        SelectArgs sel;
-        memset(&sel, 0, sizeof sel);
-        sel.scores = coarse.as<float>();
-        sel.pitch = pitch;
-        sel.nlist = nlist;
-        sel.nprobe = nprobe;
-        sel.probes = a.sort_probes ? nullptr : d_probes;
-        sel.probe_keys = d_keys;
-        sel.eps = ea;
-        if (use_tc_coarse) {
-            sel.eps.rel = IVF_REL_EPS;
-            sel.eps.nonneg = (ix.cent_nonneg && q_nonneg) ? 1 : 0;
-            sel.eps.max_norm = ix.cent_max_norm;
-        }
-        sel.exact_all = a.sort_probes ? 1 : 0;
-        sel.q_off = q_off.as<int64_t>();
-        sel.q_idx = q_idx.as<uint16_t>();
-        sel.q_val = q_val.as<float>();
-        sel.cent = ix.cent.as<float>();
-        sel.d = d;
-        // lists that fit the unconditional first scan round (c0 scores, see below), with some slack
-        sel.n_front = (ix.nstored > 0 && h->opt_front_probes)
-                          ? (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, 3 * (int64_t)h->opt_round0_scores * nlist / (4 * ix.nstored)))
-                          : 0;
-        select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(sel);
-        SOLO_CUDA(cudaGetLastError());
-        if (a.sort_probes) {
-            SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
-            int npad = 1;
-            while (npad < nprobe) npad <<= 1;
-            size_t sm2 = (size_t)npad * sizeof(unsigned long long);
-            SOLO_CUDA(cudaFuncSetAttribute(sort_probe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-            sort_probe_rows_kernel<<<nq, 512, sm2, st>>>(d_keys, nprobe, npad, d_probes);
+        {
+            StageTimer t(h, ST_PROBE_SELECT, 1 + (a.sort_probes ? 1 : 0));
+            size_t smem = (size_t)nlist * sizeof(uint32_t);
+            SOLO_CUDA(cudaFuncSetAttribute(select_probes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned long long *d_keys = nullptr;
+            if (a.sort_probes) {
+                pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
+                d_keys = pkeys.as<unsigned long long>();
+            }
+            SelectArgs sel;
+            memset(&sel, 0, sizeof sel);
+            sel.scores = coarse.as<float>();
+            sel.pitch = pitch;
+            sel.nlist = nlist;
+            sel.nprobe = nprobe;
+            sel.probes = a.sort_probes ? nullptr : d_probes;
+            sel.probe_keys = d_keys;
+            sel.eps = ea;
+            if (use_tc_coarse) {
+                sel.eps.rel = IVF_REL_EPS;
+                sel.eps.nonneg = (ix.cent_nonneg && q_nonneg) ? 1 : 0;
+                sel.eps.max_norm = ix.cent_max_norm;
+            }
+            sel.exact_all = a.sort_probes ? 1 : 0;
+            sel.q_off = q_off.as<int64_t>();
+            sel.q_idx = q_idx.as<uint16_t>();
+            sel.q_val = q_val.as<float>();
+            sel.cent = ix.cent.as<float>();
+            sel.d = d;
+            // lists that fit the unconditional first scan round (c0 scores, see below), with some slack
+            sel.n_front = (ix.nstored > 0 && h->opt_front_probes)
+                              ? (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, 3 * (int64_t)h->opt_round0_scores * nlist / (4 * ix.nstored)))
+                              : 0;
+            select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(sel);
             SOLO_CUDA(cudaGetLastError());
+            if (a.sort_probes) {
+                SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
+                int npad = 1;
+                while (npad < nprobe) npad <<= 1;
+                size_t sm2 = (size_t)npad * sizeof(unsigned long long);
+                SOLO_CUDA(cudaFuncSetAttribute(sort_probe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+                sort_probe_rows_kernel<<<nq, 512, sm2, st>>>(d_keys, nprobe, npad, d_probes);
+                SOLO_CUDA(cudaGetLastError());
+            }
         }
     }
+    const int32_t *d_probes = d_probes_c;
     if (a.probes)
         SOLO_CUDA(cudaMemcpyAsync(a.probes, d_probes, (size_t)nq * nprobe * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (a.coarse_only) return;

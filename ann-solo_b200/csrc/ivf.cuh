@@ -48,6 +48,7 @@ struct IvfSearchArgs {
     int32_t *probes;     // (nq, nprobe) selected lists (unsorted set unless sort_probes)
     int sort_probes;
     int coarse_only;
+    const int32_t *given_probes;  // (nq, nprobe) device: skip coarse scoring / probe selection (mode B: another GPU selected them)
     // optional precursor-window mask fused into the (unsorted) selection output; tol_mode < 0: off
     const double *win_q_prec_mz;
     const float *win_lib_prec_mz32;

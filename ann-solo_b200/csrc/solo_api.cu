@@ -93,9 +93,23 @@ static int guarded_nohandle(char *errbuf, int errbuf_len, F &&f) {
     }
 }
 
-static void h2d(solo_handle *h, DevBuf &b, const void *src, size_t bytes) {
+static void h2d(solo_handle *h, DevBuf &b, const void *src, size_t bytes, cudaStream_t st = nullptr) {
     b.ensure(std::max<size_t>(bytes, 16));
-    if (bytes) SOLO_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (bytes) SOLO_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st ? st : h->stream));
+}
+
+// events + copy stream of the asynchronous staging API, created on first use
+static solo_handle::SlotSync &slot_sync(solo_handle *h, int slot) {
+    if (!h->copy_stream) SOLO_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    solo_handle::SlotSync &s = h->slot_sync[slot];
+    if (!s.staged) {
+        SOLO_CUDA(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+        SOLO_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        SOLO_CUDA(cudaEventCreateWithFlags(&s.fetched, cudaEventDisableTiming));
+        SOLO_CUDA(cudaMallocHost(&s.n_over, sizeof(int32_t)));
+        *s.n_over = 0;
+    }
+    return s;
 }
 
 static void drain_profile(solo_handle *h) {
@@ -297,6 +311,13 @@ void solo_destroy(solo_handle *h) {
     rel(h->r_best_row); rel(h->r_best_score); rel(h->r_n_pairs); rel(h->r_pairs); rel(h->r_n_cand); rel(h->r_ovf);
     for (auto &kv : h->parked)
         for (auto &b : kv.second.b) rel(b);
+    for (auto &kv : h->slot_sync) {
+        if (kv.second.staged) cudaEventDestroy(kv.second.staged);
+        if (kv.second.done) cudaEventDestroy(kv.second.done);
+        if (kv.second.fetched) cudaEventDestroy(kv.second.fetched);
+        if (kv.second.n_over) cudaFreeHost(kv.second.n_over);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -697,7 +718,8 @@ int solo_ivf_coarse(solo_handle *h, int charge, const float *queries, int nq, in
 // ---------------------------------------------------------------- K5 standalone
 
 static void stage_queries_impl(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_int,
-                               const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
+                               const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64,
+                               cudaStream_t st = nullptr) {
     SOLO_REQUIRE(nq >= 0 && q_off && (nq == 0 || (q_mz && q_int && q_prec_mz)), SOLO_EINVAL, "null argument");
     SOLO_REQUIRE(q_off[0] == 0, SOLO_EINVAL, "query offsets must start at 0");
     const int64_t np = q_off[nq];
@@ -711,16 +733,18 @@ static void stage_queries_impl(solo_handle *h, const float *q_mz, const void *q_
             SOLO_REQUIRE(q_mz[p] >= q_mz[p - 1], SOLO_EINVAL, "query %d: m/z not ascending", i);
     }
     SOLO_REQUIRE(maxp <= 128, SOLO_ECAPACITY, "query spectra may hold at most 128 peaks (got %d)", maxp);
-    StageTimer t(h, ST_H2D, 0, (double)(np * (8 + (q_mz_vec ? (mz_is_f64 ? 8 : 4) : 0)) + (nq + 1) * 8 + nq * 8));
+    const double h2d_bytes = (double)(np * (8 + (q_mz_vec ? (mz_is_f64 ? 8 : 4) : 0)) + (nq + 1) * 8 + nq * 8);
+    if (st) h->prof[ST_H2D].units += h2d_bytes;   // copy stream: bytes are counted, the time hides under the kernels
+    StageTimer t(h, ST_H2D, 0, h2d_bytes, /*enabled=*/st == nullptr);
     h->nq = nq;
     h->q_peaks = np;
     h->q_max_peaks = maxp;
     h->q_mz_is_f64 = mz_is_f64;
-    h2d(h, h->q_mz, q_mz, np * 4);
-    h2d(h, h->q_int, q_int, np * 4);
-    h2d(h, h->q_off, q_off, (size_t)(nq + 1) * 8);
-    h2d(h, h->q_prec_mz, q_prec_mz, (size_t)nq * 8);
-    if (q_mz_vec && (mz_is_f64 || q_mz_vec != (const void *)q_mz)) h2d(h, h->q_mz_vec, q_mz_vec, np * (mz_is_f64 ? 8 : 4));
+    h2d(h, h->q_mz, q_mz, np * 4, st);
+    h2d(h, h->q_int, q_int, np * 4, st);
+    h2d(h, h->q_off, q_off, (size_t)(nq + 1) * 8, st);
+    h2d(h, h->q_prec_mz, q_prec_mz, (size_t)nq * 8, st);
+    if (q_mz_vec && (mz_is_f64 || q_mz_vec != (const void *)q_mz)) h2d(h, h->q_mz_vec, q_mz_vec, np * (mz_is_f64 ? 8 : 4), st);
     else h->q_mz_is_f64 = -1;  // binning reads the float32 scorer array
 }
 
@@ -828,6 +852,22 @@ int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p) 
         SOLO_REQUIRE(p->max_pairs > 0, SOLO_EINVAL, "max_pairs must be positive");
         ensure_results(h, nq, p->max_pairs);
         if (nq == 0) return;
+        // an asynchronously staged batch (solo_stage_queries_async) lands on the copy stream, and the slot's previous
+        // results may still be on their way to the host (solo_fetch_results_async): the kernels wait for both; the
+        // `done` event recorded behind the last kernel is what later copies of this slot wait for
+        auto sync_it = h->slot_sync.find(h->active_slot);
+        if (sync_it != h->slot_sync.end()) {
+            if (sync_it->second.wait_staged) SOLO_CUDA(cudaStreamWaitEvent(h->stream, sync_it->second.staged, 0));
+            if (sync_it->second.has_fetched) SOLO_CUDA(cudaStreamWaitEvent(h->stream, sync_it->second.fetched, 0));
+            sync_it->second.wait_staged = false;
+        }
+        struct DoneMark {
+            solo_handle *h;
+            ~DoneMark() {
+                auto it = h->slot_sync.find(h->active_slot);
+                if (it != h->slot_sync.end() && cudaEventRecord(it->second.done, h->stream) == cudaSuccess) it->second.has_done = true;
+            }
+        } done_mark{h};
         DevBuf &ovf = h->r_ovf;
         ovf.ensure(16);
         SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
@@ -959,6 +999,57 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
     rc = solo_search_staged(h, charge, p);
     if (rc) return rc;
     return solo_fetch_results(h, best_row, best_score, n_pairs, pairs, n_cand);
+}
+
+// ---- streaming: copies of batch i+1 / i-1 under the kernels of batch i ------------------------------------------
+int solo_stage_queries_async(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
+                             const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        solo_handle::SlotSync &s = slot_sync(h, h->active_slot);
+        // the slot's previous batch must have been read by its kernels before its buffers are overwritten
+        if (s.has_done) SOLO_CUDA(cudaStreamWaitEvent(h->copy_stream, s.done, 0));
+        stage_queries_impl(h, q_mz, q_mz_vec ? q_mz_vec : q_mz, q_intensity, q_off, q_prec_mz, nq, mz_is_f64, h->copy_stream);
+        SOLO_CUDA(cudaEventRecord(s.staged, h->copy_stream));
+        s.wait_staged = true;
+    });
+}
+
+int solo_fetch_results_async(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs,
+                             int32_t *n_cand) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        solo_handle::SlotSync &s = slot_sync(h, h->active_slot);
+        const int nq = h->r_nq;
+        if (!s.has_done) {   // nothing was searched through the event-marked path: order behind the compute stream
+            SOLO_CUDA(cudaEventRecord(s.done, h->stream));
+            s.has_done = true;
+        }
+        SOLO_CUDA(cudaStreamWaitEvent(h->copy_stream, s.done, 0));
+        auto cp = [&](void *dst, const DevBuf &src, size_t bytes) {
+            if (dst && bytes) SOLO_CUDA(cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+        };
+        cp(best_row, h->r_best_row, (size_t)nq * 4);
+        cp(best_score, h->r_best_score, (size_t)nq * 8);
+        cp(n_pairs, h->r_n_pairs, (size_t)nq * 4);
+        cp(pairs, h->r_pairs, (size_t)nq * h->r_max_pairs * 8);
+        cp(n_cand, h->r_n_cand, (size_t)nq * 4);
+        if (nq) cp(s.n_over, h->r_ovf, 4);
+        h->prof[ST_D2H].units += (double)nq * (4 + 8 + 4 + 4 + (double)h->r_max_pairs * 8);
+        SOLO_CUDA(cudaEventRecord(s.fetched, h->copy_stream));
+        s.has_fetched = true;
+    });
+}
+
+int solo_wait_results(solo_handle *h, int slot) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        auto it = h->slot_sync.find(slot);
+        SOLO_REQUIRE(it != h->slot_sync.end() && it->second.has_fetched, SOLO_ESTATE, "slot %d has no fetch in flight", slot);
+        SOLO_CUDA(cudaEventSynchronize(it->second.fetched));
+        h->k5_overflow_pairs += *it->second.n_over;
+        *it->second.n_over = 0;
+    });
 }
 
 // ---- K0 / .splib: ingestion -----------------------------------------------------------------
@@ -1348,6 +1439,61 @@ int solo_ivf_search_staged(solo_handle *h, int charge, int k, int nprobe, int64_
         s.nq = nq;
         s.k = k;
         s.nprobe = nprobe;
+        s.I = d_I;
+        s.D = d_D;
+        s.win_tol_mode = -1;
+        ivf_search(h, ix, s);
+    });
+}
+
+int solo_ivf_probe_staged(solo_handle *h, int charge, int nprobe, int q_begin, int nq_slice, int32_t *d_probes) {
+    if (!h || !d_probes) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
+        SOLO_REQUIRE(q_begin >= 0 && nq_slice >= 0 && q_begin + nq_slice <= h->nq, SOLO_EINVAL, "query slice out of range");
+        if (nq_slice == 0) return;
+        DevBuf &qv = h->scratch[19];
+        qv.ensure((size_t)h->nq * h->hash_len * sizeof(float));
+        float *qs = qv.as<float>() + (size_t)q_begin * h->hash_len;
+        const void *mzv = h->q_mz_is_f64 < 0 ? h->q_mz.p : h->q_mz_vec.p;
+        // CSR offsets are absolute: a shifted view of the offsets is a valid batch over the same peak arrays
+        launch_vectorize(h, mzv, h->q_mz_is_f64 > 0 ? 1 : 0, h->q_int.as<float>(), h->q_off.as<int64_t>() + q_begin, nq_slice,
+                         h->q_peaks, 1, qs, nullptr, 0);
+        IvfSearchArgs s;
+        memset(&s, 0, sizeof s);
+        s.q = qs;
+        s.nq = nq_slice;
+        s.k = 1;
+        s.nprobe = nprobe;
+        s.probes = d_probes;
+        s.coarse_only = 1;
+        s.win_tol_mode = -1;
+        ivf_search(h, ix, s);
+    });
+}
+
+int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const int32_t *d_probes, int64_t *d_I, float *d_D) {
+    if (!h || !d_I || !d_probes) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        IvfIndex &ix = get_ivf(h, charge, true);
+        SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
+        SOLO_REQUIRE(nprobe >= 1 && nprobe <= ix.nlist, SOLO_EINVAL, "the given probe rows hold %d lists, the index has %d",
+                     nprobe, ix.nlist);
+        const int nq = h->nq;
+        if (nq == 0) return;
+        DevBuf &qv = h->scratch[19];
+        qv.ensure((size_t)nq * h->hash_len * sizeof(float));
+        const void *mzv = h->q_mz_is_f64 < 0 ? h->q_mz.p : h->q_mz_vec.p;
+        launch_vectorize(h, mzv, h->q_mz_is_f64 > 0 ? 1 : 0, h->q_int.as<float>(), h->q_off.as<int64_t>(), nq, h->q_peaks,
+                         1, qv.as<float>(), nullptr, 0);
+        IvfSearchArgs s;
+        memset(&s, 0, sizeof s);
+        s.q = qv.as<float>();
+        s.nq = nq;
+        s.k = k;
+        s.nprobe = nprobe;
+        s.given_probes = d_probes;
         s.I = d_I;
         s.D = d_D;
         s.win_tol_mode = -1;

@@ -223,6 +223,15 @@ struct solo_handle {
     };
     int active_slot = 0;
     std::map<int, Slot> parked;
+    // asynchronous staging / fetching (solo_stage_queries_async, solo_fetch_results_async): a copy stream of its
+    // own and three events per slot order it against the compute stream
+    struct SlotSync {
+        cudaEvent_t staged = nullptr, done = nullptr, fetched = nullptr;
+        bool wait_staged = false, has_done = false, has_fetched = false;
+        int32_t *n_over = nullptr;   // pinned
+    };
+    cudaStream_t copy_stream = nullptr;
+    std::map<int, SlotSync> slot_sync;
 };
 
 namespace solo {
@@ -232,7 +241,8 @@ struct StageTimer {
     solo_handle *h;
     int st;
     cudaEvent_t a = nullptr, b = nullptr;
-    StageTimer(solo_handle *h_, int st_, int64_t launches, double units = 0.0) : h(h_), st(st_) {
+    StageTimer(solo_handle *h_, int st_, int64_t launches, double units = 0.0, bool enabled = true) : h(h_), st(st_) {
+        if (!enabled) return;
         h->launches += launches;
         h->prof[st].launches += launches;
         h->prof[st].units += units;

@@ -59,7 +59,14 @@ class SoloEngine:
             pass
 
     def set_stream(self, cuda_stream: Optional[int]):
-        self._check(self._lib.solo_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Run this engine's kernels and copies on the given CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``);
+        None: the engine's own non-blocking stream. Handle 0 is CUDA's legacy default stream — torch's default current
+        stream — and is passed as cudaStreamLegacy so that it is not mistaken for "none"."""
+        if cuda_stream is None:
+            handle = None
+        else:
+            handle = C.c_void_p(1 if int(cuda_stream) == 0 else int(cuda_stream))   # 0x1 = cudaStreamLegacy
+        self._check(self._lib.solo_set_stream(self._h, handle))
 
     def set_option(self, key: str, value: int):
         self._check(self._lib.solo_set_option(self._h, key.encode(), int(value)))
@@ -279,6 +286,69 @@ class SoloEngine:
         self.search_staged(charge, params)
         return self.fetch_results(out)
 
+    # ------------------------------------------------------------------ streaming
+    def stage_queries_async(self, q: dict, mz_vec: Optional[np.ndarray] = None):
+        """stage_queries on the engine's copy stream (returns at once). The arrays should be page-locked and must not
+        change until the batch has been searched; they are kept referenced here."""
+        qmz = _c(q["mz"], np.float32)
+        qin = _c(q["inten"], np.float32)
+        qoff = _c(q["off"], np.int64)
+        qpm = _c(q["prec_mz"], np.float64)
+        is64 = mz_vec is not None and mz_vec.dtype == np.float64
+        if mz_vec is not None:
+            mz_vec = _c(mz_vec, np.float64 if is64 else np.float32)
+        self._staged = (qmz, qin, qoff, qpm, mz_vec)
+        self._staged_nq = len(qoff) - 1
+        self._check(self._lib.solo_stage_queries_async(self._h, _ptr(qmz), _ptr(mz_vec), _ptr(qin), _ptr(qoff), _ptr(qpm),
+                                                       self._staged_nq, int(is64)))
+
+    def fetch_results_async(self, out: Optional[dict] = None) -> dict:
+        """Queue the device->host copies of the active slot's results behind its kernels, on the copy stream; the
+        arrays are valid after ``wait_results(slot)``."""
+        nq, mp = self._staged_nq, self._staged_max_pairs
+        if out is None:
+            out = dict(best_row=np.empty(nq, np.int32), score=np.empty(nq, np.float64),
+                       n_pairs=np.empty(nq, np.int32), pairs=np.empty((nq, mp, 2), np.uint32),
+                       n_cand=np.empty(nq, np.int32))
+        self._check(self._lib.solo_fetch_results_async(self._h, _ptr(out["best_row"]), _ptr(out["score"]),
+                                                       _ptr(out["n_pairs"]), _ptr(out["pairs"]), _ptr(out["n_cand"])))
+        return out
+
+    def wait_results(self, slot: int):
+        self._check(self._lib.solo_wait_results(self._h, int(slot)))
+
+    def search_stream(self, params: SearchParams, batches, slots=(9001, 9002)):
+        """The reference's batch loop (spectral_library.py:301-306) as a software pipeline: ``batches`` yields
+        ``(charge, q, out)`` — a host peak store, optionally the float64 m/z under ``q['mz_vec']``, and an optional
+        dict of result arrays to fill (page-locked buffers make the copies asynchronous). The host->device copy of
+        batch i+1 and the device->host copy of batch i-1 run on the copy stream under the kernels of batch i.
+        Yields ``(charge, results)`` in input order; the result arrays of a batch are complete when it is yielded."""
+        it = iter(batches)
+        prev_slot = self._slot if hasattr(self, "_slot") else 0
+        nxt = next(it, None)
+        if nxt is not None:
+            self.select_slot(slots[0])
+            self.stage_queries_async(nxt[1], nxt[1].get("mz_vec"))
+        i = 0
+        pending = None   # (slot, charge, out) of the batch whose fetch is in flight
+        while nxt is not None:
+            cur, nxt = nxt, next(it, None)
+            if nxt is not None:
+                self.select_slot(slots[(i + 1) % 2])
+                self.stage_queries_async(nxt[1], nxt[1].get("mz_vec"))
+            self.select_slot(slots[i % 2])
+            self.search_staged(cur[0], params)
+            out = self.fetch_results_async(cur[2] if len(cur) > 2 else None)
+            if pending is not None:
+                self.wait_results(pending[0])
+                yield pending[1], pending[2]
+            pending = (slots[i % 2], cur[0], out)
+            i += 1
+        if pending is not None:
+            self.wait_results(pending[0])
+            yield pending[1], pending[2]
+        self.select_slot(prev_slot)
+
     # ------------------------------------------------------------------ K0: process_spectrum, batched
     def process_spectra(self, store: dict, min_mz=11.0, max_mz=2010.0, min_peaks=10, min_mz_range=250.0,
                         remove_precursor=False, remove_precursor_tolerance=0.0, min_intensity=0.01, max_peaks=50,
@@ -380,6 +450,17 @@ class SoloEngine:
         int64 / float32 buffers (e.g. torch tensors' data_ptr())."""
         self._check(self._lib.solo_ivf_search_staged(self._h, int(charge), int(k), int(nprobe), C.c_void_p(d_I),
                                                      C.c_void_p(d_D)))
+
+    def ivf_probe_staged(self, charge: int, nprobe: int, q_begin: int, nq_slice: int, d_probes: int):
+        """Coarse scoring + probe selection for the staged queries [q_begin, q_begin + nq_slice): d_probes is a
+        device pointer of an (nq_slice, nprobe) int32 buffer."""
+        self._check(self._lib.solo_ivf_probe_staged(self._h, int(charge), int(nprobe), int(q_begin), int(nq_slice),
+                                                    C.c_void_p(d_probes)))
+
+    def ivf_scan_staged(self, charge: int, k: int, nprobe: int, d_probes: int, d_I: int, d_D: int):
+        """Scan this GPU's lists for every staged query with given probe rows d_probes (nq, nprobe) int32."""
+        self._check(self._lib.solo_ivf_scan_staged(self._h, int(charge), int(k), int(nprobe), C.c_void_p(d_probes),
+                                                   C.c_void_p(d_I), C.c_void_p(d_D)))
 
     def merge_topk_device(self, d_D_parts: int, d_I_parts: int, parts: int, nq: int, k: int, q_begin: int, nq_out: int,
                           d_D: int, d_I: int):

@@ -4,9 +4,10 @@ Mode A (library fits in HBM): the library and index are replicat
 every batch are partitioned contiguously by rank, there is NO collective on the data path; the
 per-rank results are gathered to rank 0 once.
 
-Mode B (IVF lists sharded): every rank scans only the lists it owns; the per-rank top-k
-(score, id) rows are exchanged with one all-gather and merged under the same total order
-(score desc, id asc), so the merged top-k equals the single-GPU top-k exactly.
+Mode B (IVF lists sharded): coarse scoring is sharded by queries (probe rows all-gathered), every
+rank scans only the lists it owns, the per-rank top-k (score, id) rows travel to the rank that owns the
+query slice with one all-to-all and are merged there under the same total order (score desc, id asc),
+so the merged top-k equals the single-GPU top-k exactly.
 """
 from __future__ import annotations
 
@@ -93,47 +94,83 @@ def allgather_topk(D: np.ndarray, I: np.ndarray, k: int):
     return merge_topk([t.cpu().numpy() for t in gD], [t.cpu().numpy() for t in gI], k)
 
 
-def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world: int = 1, group=None,
-                         peers=None) -> dict:
-    """Mode B for one batch: every GPU holds the whole query batch and a shard of the inverted
-    lists (``SoloEngine.ivf_set_owned_lists``). Each GPU scans its lists (device top-k rows), the
-    rows are exchanged with ONE all-gather (NCCL over NVLink), every GPU merges and finishes
-    (precursor window, best match) its contiguous slice of the queries on the device. Returns the
-    slice's results (rows ``shard_bounds(nq, rank, world)``).
+def slice_bounds(n: int, rank: int, world: int):
+    """Mode B query slices: equal length ceil(n / world) (what all_gather_into_tensor / all_to_all_single
+    exchange), the last ones clipped at n. Returns (begin, end, slice_len)."""
+    s = -(-n // world) if n else 0
+    b = min(rank * s, n)
+    return b, min(b + s, n), s
 
-    ``peers``: single-process variant used by the one-GPU test — a list of engines standing in for
-    the ranks (each owning some lists); the exchange is a concatenation instead of a collective.
+
+def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world: int = 1, group=None,
+                         peers=None, mz_vec: Optional[np.ndarray] = None, stats: Optional[dict] = None):
+    """Mode B for one batch: every GPU holds the whole query batch and a shard of the inverted lists
+    (``SoloEngine.ivf_set_owned_lists``). Work is split twice:
+
+    1. coarse scoring + probe selection by QUERIES: rank r does it for its slice, the (slice, nprobe) int32 rows
+       are all-gathered (NCCL over NVLink) — every GPU then knows every query's lists;
+    2. the list scan + exact top-k by LISTS: every GPU scans the lists it owns for all queries;
+    3. the per-GPU top-k rows go to the GPU that owns the query slice with ONE all-to-all (rank r receives only
+       its slice's rows from every peer: Q k 12 / world bytes per peer instead of the whole (Q, k) tensor);
+    4. every GPU merges its slice under (score desc, id asc) and finishes it (precursor window, best match).
+
+    Everything runs on the engine's stream = torch's current stream, so the collectives are ordered behind the
+    kernels without host synchronisation. Returns (results of the slice, (merged D, merged I)); the merged top-k
+    equals the single-GPU top-k bit for bit.
+
+    ``peers``: single-process variant used by the one-GPU test — a list of engines standing in for the ranks (each
+    owning some lists); the exchanges are tensor copies instead of collectives.
     """
     import torch
     dev = torch.device("cuda", eng.device)
     nq = len(q["off"]) - 1
-    k = params.k
+    k, nprobe = params.k, params.nprobe
     engines = peers if peers is not None else [eng]
-    parts_D, parts_I = [], []
+    parts = len(peers) if peers is not None else world
+    S = slice_bounds(nq, 0, parts)[2]
+    stream = torch.cuda.current_stream(dev).cuda_stream
     for e in engines:
-        e.stage_queries(q)
-        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        e.ivf_search_staged(charge, k, params.nprobe, I.data_ptr(), D.data_ptr())
-        e.synchronize()
-        parts_D.append(D)
-        parts_I.append(I)
+        e.set_stream(stream)
+        e.stage_queries(q, mz_vec)
+    # 1. probes, sharded by queries
+    probes_all = torch.zeros((parts * S, nprobe), dtype=torch.int32, device=dev)
     if peers is not None:
-        all_D, all_I, parts = torch.stack(parts_D), torch.stack(parts_I), len(peers)
-    elif world > 1:
-        import torch.distributed as dist
-        all_D = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        all_I = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_D, parts_D[0], group=group)
-        dist.all_gather_into_tensor(all_I, parts_I[0], group=group)
-        torch.cuda.synchronize(dev)
-        parts = world
+        for r, e in enumerate(engines):
+            b, en, _ = slice_bounds(nq, r, parts)
+            e.ivf_probe_staged(charge, nprobe, b, en - b, probes_all[r * S:].data_ptr())
     else:
-        all_D, all_I, parts = parts_D[0][None], parts_I[0][None], 1
-    b, e_ = shard_bounds(nq, rank, world)
-    mD = torch.empty((e_ - b, k), dtype=torch.float32, device=dev)
-    mI = torch.empty((e_ - b, k), dtype=torch.int64, device=dev)
-    eng.merge_topk_device(all_D.data_ptr(), all_I.data_ptr(), parts, nq, k, b, e_ - b, mD.data_ptr(), mI.data_ptr())
-    eng.score_staged_ids(charge, params, mI.data_ptr(), b, e_ - b)
+        b, en, _ = slice_bounds(nq, rank, world)
+        if world > 1:
+            import torch.distributed as dist
+            mine = torch.zeros((S, nprobe), dtype=torch.int32, device=dev)
+            eng.ivf_probe_staged(charge, nprobe, b, en - b, mine.data_ptr())
+            dist.all_gather_into_tensor(probes_all, mine, group=group)
+        else:
+            eng.ivf_probe_staged(charge, nprobe, b, en - b, probes_all.data_ptr())
+    # 2. scan of the owned lists for every query, 3. exchange towards the owner of each query slice
+    recv_D = torch.empty((parts, S, k), dtype=torch.float32, device=dev)
+    recv_I = torch.empty((parts, S, k), dtype=torch.int64, device=dev)
+    my = rank
+    for r, e in enumerate(engines):
+        loc_D = torch.full((parts * S, k), float("-inf"), dtype=torch.float32, device=dev)
+        loc_I = torch.full((parts * S, k), -1, dtype=torch.int64, device=dev)
+        e.ivf_scan_staged(charge, k, nprobe, probes_all.data_ptr(), loc_I.data_ptr(), loc_D.data_ptr())
+        if peers is not None:
+            recv_D[r].copy_(loc_D[my * S:(my + 1) * S])
+            recv_I[r].copy_(loc_I[my * S:(my + 1) * S])
+        elif world > 1:
+            import torch.distributed as dist
+            dist.all_to_all_single(recv_D.view(parts * S, k), loc_D, group=group)
+            dist.all_to_all_single(recv_I.view(parts * S, k), loc_I, group=group)
+        else:
+            recv_D, recv_I = loc_D.view(1, S, k), loc_I.view(1, S, k)
+    if stats is not None:
+        stats["bytes_sent_per_rank"] = int((parts - 1) * S * (nprobe * 4 + k * 12)) if parts > 1 else 0
+    # 4. merge + finish the slice
+    b, en, _ = slice_bounds(nq, my, parts)
+    mD = torch.empty((max(en - b, 1), k), dtype=torch.float32, device=dev)
+    mI = torch.empty((max(en - b, 1), k), dtype=torch.int64, device=dev)
+    eng.merge_topk_device(recv_D.data_ptr(), recv_I.data_ptr(), parts, S, k, 0, en - b, mD.data_ptr(), mI.data_ptr())
+    eng.score_staged_ids(charge, params, mI.data_ptr(), b, en - b)
     res = eng.fetch_results()
-    return {key: v[b:e_] for key, v in res.items()}, (mD, mI)
+    return {key: v[b:en] for key, v in res.items()}, (mD[:en - b], mI[:en - b])

@@ -122,6 +122,8 @@ def run_solo(args, wl, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib, per_charge, q_by_charge = make_data(wl, rank)
+    # one non-default stream carries torch's timing events, the NCCL hand-offs and every kernel of the engine
+    torch.cuda.set_stream(torch.cuda.Stream())
     eng = SoloEngine(local_rank)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     for kv in filter(None, os.environ.get("SOLO_OPT", "").split(",")):  # tuning switches, e.g. round0_scores=6144
@@ -149,8 +151,6 @@ def run_solo(args, wl, rank, world, local_rank):
 
     max_pairs = 50
     params = SoloEngine.make_params(True, wl["k"], wl["nprobe"], OPEN_TOL, OPEN_MODE, FRAG_TOL, True, max_pairs)
-    if args.sharded:
-        return run_sharded(args, wl, rank, world, eng, charges, q_by_charge, params, torch, dist)
     # pinned host copies of the queries and of the result buffers (e2e path)
     pin_keep, host_q, host_out = [], {}, {}
     h2d_bytes = d2h_bytes = 0
@@ -191,12 +191,14 @@ def run_solo(args, wl, rank, world, local_rank):
             eng.select_slot(z)
             eng.search_staged(z, params)
 
-    def step_e2e():
-        for z in charges:
-            eng.select_slot(z)
-            eng.search_batch(z, params, host_q[z], out=host_out[z])
+    def step_e2e(n_steps=1):
+        # the public streaming call: pinned host buffers in, pinned host results out; the H2D of the next batch and
+        # the D2H of the previous one run on the copy stream under the kernels (SoloEngine.search_stream). The K
+        # timed steps are one stream of 3 K batches, like the reference's loop over config.batch_size batches.
+        for _ in eng.search_stream(params, [(z, host_q[z], host_out[z]) for _ in range(n_steps) for z in charges]):
+            pass
 
-    def timed(step_fn, steps, warmup, profile=False):
+    def timed(step_fn, steps, warmup, profile=False, streamed=False):
         for _ in range(warmup):
             step_fn()
         barrier()
@@ -217,8 +219,11 @@ def run_solo(args, wl, rank, world, local_rank):
             if ncu:
                 torch.cuda.profiler.start()
             e0.record()
-            for _ in range(steps):
-                step_fn()
+            if streamed:
+                step_fn(steps)
+            else:
+                for _ in range(steps):
+                    step_fn()
             e1.record()
             barrier()
             if ncu:
@@ -265,7 +270,7 @@ def run_solo(args, wl, rank, world, local_rank):
                 pc = np.percentile(cnt, [1, 50, 90, 99, 100]).astype(int).tolist()
                 log(f"   z={z}: scan-buffer entries/query p1/p50/p90/p99/max = {pc} mean={cnt.mean():.0f}")
     ms_res, prof, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), streamed=True)
     value = world * nq_rank * args.steps / (ms_res / 1e3)
     e2e = world * nq_rank * args.steps / (ms_e2e / 1e3)
 
@@ -273,6 +278,11 @@ def run_solo(args, wl, rank, world, local_rank):
     n_match = int(sum((host_out[z]["best_row"] >= 0).sum() for z in charges))
     assert n_match > 0.5 * nq_rank, f"only {n_match} of {nq_rank} queries matched"
 
+    # ---- mode B on the same library (N > 1, or --sharded): every rank takes part, rank 0 reports
+    sharded = None
+    if world > 1 or args.sharded:
+        sharded = measure_sharded(args, wl, rank, world, eng, charges, lib, params, torch, dist,
+                                  check_against=host_out if rank == 0 else None)
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (K3 list scan): algorithmic flops 2*d*S per query
@@ -319,6 +329,8 @@ def run_solo(args, wl, rank, world, local_rank):
     }
     if extras:
         line["extras"] = extras
+    if sharded:
+        line["sharded"] = sharded
     _emit(json.dumps(line))
     if parity and parity["mismatch"]:
         log(f"PARITY FAILURE: {parity['mismatch']} of {parity['checked']} sampled queries differ from the CPU reference path")
@@ -383,15 +395,16 @@ def measure_extras(eng, charges, q_by_charge, nq_rank, torch):
     return out
 
 
-def run_sharded(args, wl, rank, world, eng, charges, q_by_charge, params, torch, dist):
-    """Mode B: the lists of every charge are dealt to the ranks by stored-vector count,
-    every rank holds the same global query batch (seed of rank 0), scans its lists, the (Q, k) rows are
-    all-gathered over NCCL, merged on the device and every rank finishes its slice of the queries."""
+def measure_sharded(args, wl, rank, world, eng, charges, lib, params, torch, dist, check_against=None):
+    """Mode B on the same library: the inverted lists of every charge are dealt to the ranks by
+    stored-vector count, every rank holds ONE global query batch (rank 0's), coarse scoring is sharded by queries
+    (all-gather of the probe rows), the list scan by lists, the per-rank top-k rows reach the owner of each query
+    slice with one all-to-all, are merged on the device and finished there (parallel.search_batch_sharded).
+    Strong scaling: the global batch is fixed. Host query buffers are staged and the slice's results fetched every
+    step. Returns the "sharded" object on rank 0 (None elsewhere)."""
     from ann_solo_b200 import parallel, synth
-    lib = synth.make_library(wl["n_targets"], decoy_fraction=wl["decoys"], seed=1, decoy_seed=2)
-    queries = synth.make_queries(lib, wl["nq"], seed=3)
+    queries = synth.make_queries(lib, wl["nq"], seed=3)           # rank 0's batch of the mode-A run, on every rank
     q_by_charge = {z: synth.take_spectra(queries, np.flatnonzero(queries["prec_z"] == z)) for z in charges}
-    del lib
     for z in charges:
         assign = eng.ivf_assignment(z)
         nl = eng.ivf_info(z)[1]
@@ -399,45 +412,59 @@ def run_sharded(args, wl, rank, world, eng, charges, q_by_charge, params, torch,
         owner = parallel.assign_lists(sizes, world)
         eng.ivf_set_owned_lists(z, (owner == rank).astype(np.uint8))
     nq_total = sum(len(q_by_charge[z]["prec_mz"]) for z in charges)
+    stats, last = {}, {}
 
     def step():
-        n = 0
+        sent = 0
         for z in charges:
-            res, _ = parallel.search_batch_sharded(eng, z, params, q_by_charge[z], rank, world)
-            n += int((res["best_row"] >= 0).sum())
-        return n
+            res, _ = parallel.search_batch_sharded(eng, z, params, q_by_charge[z], rank, world, stats=stats)
+            last[z] = res
+            sent += stats.get("bytes_sent_per_rank", 0)
+        return sent
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 2)):
         step()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    torch.cuda.synchronize()
+    eng.profile_reset()
+    eng.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    matched = 0
+    sent = 0
     for _ in range(args.steps):
-        matched = step()
+        sent = step()
     e1.record()
     torch.cuda.synchronize()
+    prof = eng.profile()
+    eng.profile_enable(False)
+    matched = sum(int((last[z]["best_row"] >= 0).sum()) for z in charges)
+    mismatch = None
+    if check_against is not None:      # rank 0: its slice against the replicated (mode A) results of the same batch
+        mismatch = 0
+        for z in charges:
+            b, e, _ = parallel.slice_bounds(len(q_by_charge[z]["prec_mz"]), rank, world)
+            for key in ("best_row", "n_cand", "n_pairs"):
+                mismatch += int((last[z][key] != check_against[z][key][b:e]).sum())
+            mismatch += int((last[z]["score"].view(np.uint64) != check_against[z]["score"][b:e].view(np.uint64)).sum())
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     m = torch.tensor([matched], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(m)
+    for z in charges:
+        eng.ivf_set_owned_lists(z, None)
     if rank != 0:
-        return
+        return None
     ms = float(t.item())
-    v = nq_total * args.steps / (ms / 1e3)
-    _emit(json.dumps({
-        "metric": "query spectra/sec, cascade open search", "value": round(v, 1), "unit": "spectra/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "global_batch": nq_total, "nlist": wl["nlist"], "nprobe": wl["nprobe"],
-                   "k": wl["k"], "parallelism": f"mode B: inverted lists sharded x{world}, NCCL all-gather of top-k rows, "
-                                                "device merge, queries finished by slice"},
-        "e2e": {"value": round(v, 1), "unit": "spectra/s", "note": "host query buffers staged every step"},
-        "matched_queries": int(m.item()),
-    }))
+    return {"value": round(nq_total * args.steps / (ms / 1e3), 1), "unit": "spectra/s", "ms_per_step": round(ms / args.steps, 3),
+            "scaling": "strong", "global_batch": nq_total, "matched_queries": int(m.item()),
+            "bytes_sent_per_rank_per_step": int(sent),
+            "exchange": "all-gather of probe rows (int32) + all-to-all of top-k rows (f32 score, i64 id) over NCCL",
+            "stage_ms_per_step_rank0": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0},
+            "mismatch_vs_replicated": mismatch,
+            "note": "inverted lists sharded x%d; host query buffers staged and the slice's results fetched every step" % world}
 
 
 def cpu_pipeline(o, store, q, cent, assign, nlist, wl, charge, threads, use_ref, simd=True):

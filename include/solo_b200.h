@@ -289,6 +289,19 @@ int solo_ssm_features(solo_handle *h, int charge, const void *q_mz, int q_mz_is_
 int solo_ssm_features_staged(solo_handle *h, int charge, const int32_t *q_prec_charge,
                              const int32_t *sequence_len, double *out);
 
+/* ---- streaming (reference: the batch loop of _search_cascade, spectral_library.py:301-306) -----------------
+ * The same three steps as solo_search_batch, split so that the copies of neighbouring batches hide under the
+ * kernels: staging and fetching run on a copy stream of the handle's own, ordered against the compute stream by
+ * events per query slot (solo_select_slot). Host buffers must be page-locked for the copies to overlap and must
+ * stay untouched until solo_wait_results(slot) returns. Typical loop with two slots:
+ *   select(s[(i+1)%2]); stage_async(batch i+1);  select(s[i%2]); search_staged(batch i); fetch_async(out i);
+ *   wait_results(s[(i-1)%2]);  -> results of batch i-1 are on the host */
+int solo_stage_queries_async(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
+                             const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64);
+int solo_fetch_results_async(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs,
+                             int32_t *n_cand);
+int solo_wait_results(solo_handle *h, int slot);
+
 /* ---- mode B: inverted lists sharded over GPUs ---------------------
  * The reference has no multi-GPU path; these entry points are what a one-process-per-GPU driver
  * needs around its collective (NCCL all-gather of the per-GPU top-k rows). All pointers named d_*
@@ -299,6 +312,14 @@ int solo_ivf_set_owned_lists(solo_handle *h, int charge, const uint8_t *owned, i
 /* Vectorise the staged query batch and search this GPU's lists: d_I (nq,k) int64 / d_D (nq,k)
  * float32, sorted (score desc, id asc), padded with -1 / -inf. */
 int solo_ivf_search_staged(solo_handle *h, int charge, int k, int nprobe, int64_t *d_I, float *d_D);
+/* The same search split at the probe set, so that coarse scoring is sharded by QUERIES and the list scan by LISTS:
+ * solo_ivf_probe_staged vectorises the staged queries [q_begin, q_begin + nq_slice) and writes their nprobe selected
+ * lists (closest first, like the single-GPU path) to d_probes (nq_slice, nprobe) int32; after the ranks exchanged
+ * their rows (all-gather), solo_ivf_scan_staged scans this GPU's lists for ALL staged queries with the given
+ * d_probes (nq, nprobe) and leaves the local top-k like solo_ivf_search_staged. */
+int solo_ivf_probe_staged(solo_handle *h, int charge, int nprobe, int q_begin, int nq_slice, int32_t *d_probes);
+int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const int32_t *d_probes, int64_t *d_I,
+                         float *d_D);
 /* Merge `parts` such results, laid out (parts, nq, k) as all_gather_into_tensor leaves them, for the
  * queries [q_begin, q_begin + nq_out): d_D/d_I (nq_out, k), same order and padding. */
 int solo_merge_topk_device(solo_handle *h, const float *d_D_parts, const int64_t *d_I_parts, int parts, int nq, int k,

@@ -44,7 +44,7 @@ def test_sharded_lists_equal_single_gpu(engine, oracle, synth, world):
     got = {}
     for r in range(world):  # every "rank" merges and finishes its own slice of the queries
         res, (mD, mI) = parallel.search_batch_sharded(peers[r], charge, params, q, rank=r, world=world, peers=peers)
-        b, e_ = parallel.shard_bounds(nq, r, world)
+        b, e_, _ = parallel.slice_bounds(nq, r, world)
         assert np.array_equal(mI.cpu().numpy(), I_ref[b:e_]), "merged ids differ from the single-GPU top-k"
         assert np.array_equal(mD.cpu().numpy().view(np.uint32), D_ref[b:e_].view(np.uint32))
         for key, v in res.items():
