@@ -108,7 +108,8 @@ SYMBOLS = {
     "solo_ivf_set_owned_lists": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "solo_ivf_search_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "solo_ivf_probe_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
-    "solo_ivf_scan_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "solo_ivf_scan_staged": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "solo_merge_score_staged": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "solo_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "solo_score_staged_ids": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, C.c_int, C.c_int]),
     "solo_profile_enable": (C.c_int, [_vp, C.c_int]),

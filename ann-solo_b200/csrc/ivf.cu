@@ -776,6 +776,9 @@ struct FinalArgs {
     // fused output
     int32_t *sel_ids;
     int32_t *sel_cnt;
+    // mode B exchange format: (nq, k) entries (float score bits << 32 | row id), unsorted, padded with IVF_PACKED_PAD;
+    // the score is the approximate one (exact for entries that went through the band) — within eps of the exact score
+    unsigned long long *packed;
     // optional precursor-window mask (applied after the top-k)
     const double *q_prec_mz;
     const float *lib_prec_mz32;
@@ -845,6 +848,15 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     const int n = raw;
     const int kk = min(a.k, n);
     const bool sorted_out = a.I != nullptr;
+    // list position -> library row (the merge of mode B runs on row ids directly: list_ids == null)
+    auto row_of = [&](uint32_t pos) -> int { return a.list_ids ? a.list_ids[pos] : (int)pos; };
+    auto emit = [&](int id, float score) {
+        if (a.packed)
+            a.packed[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] =
+                ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(uint32_t)id;
+        else if (window_pass(a, q, id))
+            a.sel_ids[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] = id;
+    };
     if (threadIdx.x == 0) {
         s_nout = 0;
         s_neq = 0;
@@ -866,8 +878,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
             const float s = ivf_o2f(s_keys[i]);
             if (s > hi) {
                 atomicAdd(&s_ncert, 1);
-                const int id = a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)];
-                if (window_pass(a, q, id)) a.sel_ids[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] = id;
+                emit(row_of((uint32_t)(b[i] & 0xFFFFFFFFull)), s);
             } else if (s >= lo) {
                 const int p = atomicAdd(&s_nband, 1);
                 if (p < TK_BCAP) s_band_pos[p] = (uint32_t)(b[i] & 0xFFFFFFFFull);
@@ -891,7 +902,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
                 }
                 if (lane == 0)
                     s_band_key[w] = ((unsigned long long)((acc == acc) ? ivf_f2o(acc) : 0u) << 32) |
-                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)a.list_ids[pos]);
+                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)row_of(pos));
             }
             __syncthreads();
             const int need = kk - s_ncert;
@@ -899,13 +910,14 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
                 const unsigned long long key = s_band_key[w];
                 int r = 0;
                 for (int w2 = 0; w2 < nband; ++w2) r += s_band_key[w2] > key;
-                if (r < need) {
-                    const int id = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
-                    if (window_pass(a, q, id)) a.sel_ids[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] = id;
-                }
+                if (r < need) emit((int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)), ivf_o2f((uint32_t)(key >> 32)));
             }
             __syncthreads();
-            if (threadIdx.x == 0) a.sel_cnt[q] = s_nout;
+            if (a.packed) {
+                for (int i = s_nout + threadIdx.x; i < a.k; i += blockDim.x) a.packed[(int64_t)q * a.k + i] = IVF_PACKED_PAD;
+            } else if (threadIdx.x == 0) {
+                a.sel_cnt[q] = s_nout;
+            }
             return;
         }
         __syncthreads();  // band larger than the on-chip list: generic path below (s_keys still hold approximate keys)
@@ -941,13 +953,12 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
             n_eq_local += (key == T2);
             if (key > T2) {  // strictly better than the k-th: in
                 const unsigned long long e = b[i];
-                const int id = a.list_ids[(uint32_t)(e & 0xFFFFFFFFull)];
+                const int id = row_of((uint32_t)(e & 0xFFFFFFFFull));
                 if (sorted_out) {
                     int slot = atomicAdd(&s_nout, 1);
                     s_sorted[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
-                } else if (window_pass(a, q, id)) {
-                    int slot = atomicAdd(&s_nout, 1);
-                    a.sel_ids[(int64_t)q * a.k + slot] = id;
+                } else {   // a "certainly in" key carries no score: the entry's own (approximate) one is reported
+                    emit(id, key == 0xFFFFFFFFu ? __uint_as_float((uint32_t)(e >> 32)) : ivf_o2f(key));
                 }
             }
         }
@@ -958,7 +969,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
         uint32_t Tid = 1u;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t key = s_keys[i];
-            s_keys[i] = (key == T2) ? 0xFFFFFFFEu - (uint32_t)a.list_ids[(uint32_t)(b[i] & 0xFFFFFFFFull)] : 0u;
+            s_keys[i] = (key == T2) ? 0xFFFFFFFEu - (uint32_t)row_of((uint32_t)(b[i] & 0xFFFFFFFFull)) : 0u;
         }
         __syncthreads();
         if (neq > need_eq) {
@@ -972,16 +983,19 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
                 if (sorted_out) {
                     int slot = atomicAdd(&s_nout, 1);
                     s_sorted[slot] = ((unsigned long long)T2 << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
-                } else if (window_pass(a, q, id)) {
-                    int slot = atomicAdd(&s_nout, 1);
-                    a.sel_ids[(int64_t)q * a.k + slot] = id;
+                } else {
+                    emit(id, ivf_o2f(T2));
                 }
             }
         }
     }
     __syncthreads();
     if (!sorted_out) {
-        if (threadIdx.x == 0) a.sel_cnt[q] = s_nout;
+        if (a.packed) {
+            for (int i = s_nout + threadIdx.x; i < a.k; i += blockDim.x) a.packed[(int64_t)q * a.k + i] = IVF_PACKED_PAD;
+        } else if (threadIdx.x == 0) {
+            a.sel_cnt[q] = s_nout;
+        }
         return;
     }
     int npad = 1;
@@ -1422,6 +1436,8 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         ea.rel = IVF_REL_EPS;
         ea.nonneg = (ix.nonneg && q_nonneg) ? 1 : 0;
     }
+    ix.last_eps_rel = ea.rel;
+    ix.last_eps_nonneg = ea.nonneg;
 
     ScanArgs sa;
     sa.gq = gq.as<int32_t>();
@@ -1484,6 +1500,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     fa.D = a.D;
     fa.sel_ids = a.sel_ids;
     fa.sel_cnt = a.sel_cnt;
+    fa.packed = a.packed;
     fa.tol_mode = -1;
     fa.eps = ea;
     fa.q = a.q;
@@ -1491,7 +1508,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     fa.sp_off = ix.sp_off.as<int64_t>();
     fa.sp_idx = ix.sp_idx.as<uint16_t>();
     fa.sp_val = ix.sp_val.as<float>();
-    if (a.I == nullptr) {
+    if (a.I == nullptr && a.packed == nullptr) {
         SOLO_REQUIRE(a.sel_ids && a.sel_cnt, SOLO_EINVAL, "no output requested");
         fa.q_prec_mz = a.win_q_prec_mz;
         fa.lib_prec_mz32 = a.win_lib_prec_mz32;
@@ -1534,6 +1551,77 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
                                                           n0.as<int32_t>(), tau.as<float>(), cap, cap, a.k, ea, 1);
         SOLO_CUDA(cudaGetLastError());
     }
+}
+
+// ----------------------------------------------------------------------- mode B: merge of per-GPU top-k entries
+
+// (parts, S, k) packed entries -> per query of the slice one contiguous run of the real ones + their count
+__global__ void __launch_bounds__(256)
+merge_pack_kernel(const unsigned long long *__restrict__ parts, int n_parts, int S, int k, int cap,
+                  unsigned long long *__restrict__ buf, int32_t *__restrict__ cnt) {
+    __shared__ int s_n;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int p = 0; p < n_parts; ++p) {
+        const unsigned long long *row = parts + ((int64_t)p * S + q) * k;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const unsigned long long e = row[i];
+            if ((uint32_t)(e & 0xFFFFFFFFull) != 0xFFFFFFFFu) buf[(int64_t)q * cap + atomicAdd(&s_n, 1)] = e;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[q] = s_n;
+}
+
+// Exact top-k of the union of the GPUs' local top-k entries for the queries [q_begin, q_begin + n): the same
+// selection as K4 — k-th approximate score, entries above the band are in, the band is re-scored exactly, here
+// from the insertion-order sparse rows every GPU keeps of the whole library — with the precursor window fused in.
+void ivf_merge_select(solo_handle *h, IvfIndex &ix, const unsigned long long *d_parts, int n_parts, int S, int k,
+                      const float *d_q_slice, const float *d_qnorm_slice, int n, const IvfSearchArgs &win,
+                      int32_t *sel_ids, int32_t *sel_cnt) {
+    if (n <= 0) return;
+    const int cap = n_parts * k;
+    SOLO_REQUIRE(cap <= 32768, SOLO_ECAPACITY, "%d parts x k = %d entries per query exceed the merge capacity 32768", n_parts, cap);
+    DevBuf &buf = h->scratch[17], &cnt = h->scratch[15], &ovf = h->scratch[18];
+    buf.ensure((size_t)n * cap * sizeof(unsigned long long));
+    cnt.ensure((size_t)n * sizeof(int32_t));
+    ovf.ensure(2 * sizeof(int32_t));
+    StageTimer t(h, ST_TOPK, 2);
+    SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 2 * sizeof(int32_t), h->stream));
+    merge_pack_kernel<<<n, 256, 0, h->stream>>>(d_parts, n_parts, S, k, cap, buf.as<unsigned long long>(), cnt.as<int32_t>());
+    SOLO_CUDA(cudaGetLastError());
+    FinalArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.buf = buf.as<unsigned long long>();
+    fa.cnt = cnt.as<int32_t>();
+    fa.list_ids = nullptr;          // entries carry library rows
+    fa.cap = cap;
+    fa.k = k;
+    fa.scap = cap;
+    fa.min_cnt = -1;
+    fa.overflow = ovf.as<int32_t>();
+    fa.sel_ids = sel_ids;
+    fa.sel_cnt = sel_cnt;
+    fa.q_prec_mz = win.win_q_prec_mz;
+    fa.lib_prec_mz32 = win.win_lib_prec_mz32;
+    fa.lib_valid = win.win_lib_valid;
+    fa.charge = win.win_charge;
+    fa.tol = win.win_tol;
+    fa.tol_mode = win.win_tol_mode;
+    fa.eps.rel = ix.last_eps_rel;
+    fa.eps.nonneg = ix.last_eps_nonneg;
+    fa.eps.qnorm = d_qnorm_slice;
+    fa.eps.max_norm = ix.max_norm;
+    fa.q = d_q_slice;
+    fa.d = ix.dim;
+    fa.sp_off = ix.row_off.as<int64_t>();
+    fa.sp_idx = ix.row_idx.as<uint16_t>();
+    fa.sp_val = ix.row_val.as<float>();
+    const size_t smem = (size_t)cap * sizeof(uint32_t) + (size_t)((ix.dim + 1) & ~1) * sizeof(float);
+    SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_topk_kernel<<<n, cap <= 16384 ? 512 : TK_THREADS, smem, h->stream>>>(fa);
+    SOLO_CUDA(cudaGetLastError());
 }
 
 // ----------------------------------------------------------------------- k-means (train)

@@ -9,6 +9,7 @@ namespace solo {
 constexpr int IVF_MAX_K = 2048;        // top-k rows returned per query
 constexpr int IVF_MAX_NLIST = 32768;   // coarse scores of one query are selected in shared memory
 constexpr int64_t IVF_ROUND0_SCORES = 12288;  // scores per query appended unconditionally by scan round 0
+constexpr unsigned long long IVF_PACKED_PAD = 0xFF800000FFFFFFFFull;  // score -inf, row -1
 constexpr float IVF_REL_EPS = 1.25e-3f;  // bound on |approx - exact| / sum|q_d c_d| for the fp16 tensor path
 
 // composite selection key: larger is better; (score desc, id asc) is a strict total order
@@ -43,6 +44,7 @@ struct IvfSearchArgs {
     // outputs (any may be null)
     int64_t *I;          // (nq, k) sorted (score desc, id asc), -1 padded
     float *D;            // (nq, k) exact fp32 scores, -inf padded
+    unsigned long long *packed;  // (nq, k) unsorted (float score bits << 32 | row), IVF_PACKED_PAD padded (mode B exchange)
     int32_t *sel_ids;    // (nq, k) unsorted selected rows, first sel_cnt[q] valid
     int32_t *sel_cnt;    // (nq)
     int32_t *probes;     // (nq, nprobe) selected lists (unsorted set unless sort_probes)
@@ -78,6 +80,9 @@ void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist,
 void ivf_finalize(solo_handle *h, IvfIndex &ix);
 void ivf_reset(IvfIndex &ix);
 void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a);
+void ivf_merge_select(solo_handle *h, IvfIndex &ix, const unsigned long long *d_parts, int n_parts, int S, int k,
+                      const float *d_q_slice, const float *d_qnorm_slice, int n, const IvfSearchArgs &win,
+                      int32_t *sel_ids, int32_t *sel_cnt);
 void ivf_train(solo_handle *h, IvfIndex &ix, const float *h_x, int64_t n, int dim, int nlist, int iters,
                uint64_t seed);
 // faiss_io.cu: Faiss ".idxann" files, explicit list assignment, dense read-back

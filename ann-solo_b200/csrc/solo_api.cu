@@ -1473,8 +1473,9 @@ int solo_ivf_probe_staged(solo_handle *h, int charge, int nprobe, int q_begin, i
     });
 }
 
-int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const int32_t *d_probes, int64_t *d_I, float *d_D) {
-    if (!h || !d_I || !d_probes) return SOLO_EINVAL;
+int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const int32_t *d_probes, int64_t *d_I, float *d_D,
+                         uint64_t *d_packed) {
+    if (!h || (!d_I && !d_packed) || !d_probes) return SOLO_EINVAL;
     return guarded(h, [&] {
         IvfIndex &ix = get_ivf(h, charge, true);
         SOLO_REQUIRE(ix.dim == h->hash_len, SOLO_EINVAL, "index dim %d != hash_len %d", ix.dim, h->hash_len);
@@ -1496,6 +1497,7 @@ int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const in
         s.given_probes = d_probes;
         s.I = d_I;
         s.D = d_D;
+        s.packed = reinterpret_cast<unsigned long long *>(d_packed);
         s.win_tol_mode = -1;
         ivf_search(h, ix, s);
     });
@@ -1514,26 +1516,59 @@ int solo_merge_topk_device(solo_handle *h, const float *d_D_parts, const int64_t
     });
 }
 
+// K5 for the staged queries [q_begin, q_begin + nq_slice) over candidate rows sel (nq_slice, p->k) / r_n_cand
+static void score_slice(solo_handle *h, LibraryStore &L, const solo_search_params *p, const int32_t *sel, int q_begin,
+                        int nq_slice) {
+    DevBuf &dpos = h->scratch[23];
+    dpos.ensure((size_t)h->nq * sizeof(int32_t));
+    ScoreArgs a;
+    a.q_mz = h->q_mz.as<float>();
+    a.q_int = h->q_int.as<float>();
+    a.q_off = h->q_off.as<int64_t>() + q_begin;  // CSR offsets are absolute: a shifted view is a valid batch
+    a.q_prec_mz = h->q_prec_mz.as<double>() + q_begin;
+    a.nq = nq_slice;
+    a.q_max_peaks = h->q_max_peaks;
+    a.lib = &L;
+    a.tol = p->fragment_mz_tolerance;
+    a.allow_shift = p->allow_shift;
+    a.max_pairs = p->max_pairs;
+    a.best_pos = dpos.as<int32_t>() + q_begin;
+    a.best_row = h->r_best_row.as<int32_t>() + q_begin;
+    a.best_score = h->r_best_score.as<double>() + q_begin;
+    a.n_pairs = h->r_n_pairs.as<int32_t>() + q_begin;
+    a.pairs = h->r_pairs.as<uint32_t>() + (size_t)q_begin * p->max_pairs * 2;
+    a.overflow = h->r_ovf.as<int32_t>();
+    a.tie_by_row = 1;
+    a.cand_ids = sel;
+    a.cand_off = nullptr;
+    a.cand_cnt = h->r_n_cand.as<int32_t>() + q_begin;
+    a.cand_stride = p->k;
+    launch_best_match(h, a);
+}
+
+static void check_slice_call(solo_handle *h, int charge, LibraryStore &L, const solo_search_params *p, int q_begin,
+                             int nq_slice) {
+    const int nq = h->nq;
+    SOLO_REQUIRE(p->tol_mode == SOLO_TOL_DA || p->tol_mode == SOLO_TOL_PPM, SOLO_EINVAL, "Unknown precursor tolerance mode");
+    SOLO_REQUIRE(p->max_pairs > 0 && p->k >= 1, SOLO_EINVAL, "bad parameters");
+    SOLO_REQUIRE(q_begin >= 0 && nq_slice >= 0 && q_begin + nq_slice <= nq, SOLO_EINVAL, "query slice out of range");
+    if (h->ivf.count(charge) && h->ivf[charge].nlist > 0)
+        SOLO_REQUIRE(h->ivf[charge].ntotal == L.n, SOLO_ESTATE, "ANN index of charge %d holds %lld rows but the library has %lld",
+                     charge, (long long)h->ivf[charge].ntotal, (long long)L.n);
+    if (h->r_nq != nq || h->r_max_pairs != p->max_pairs) ensure_results(h, nq, p->max_pairs);
+    h->r_ovf.ensure(16);
+    SOLO_CUDA(cudaMemsetAsync(h->r_ovf.p, 0, 16, h->stream));
+}
+
 int solo_score_staged_ids(solo_handle *h, int charge, const solo_search_params *p, const int64_t *d_I, int q_begin,
                           int nq_slice) {
     if (!h || !p || !d_I) return SOLO_EINVAL;
     return guarded(h, [&] {
         LibraryStore &L = get_lib(h, charge);
-        const int nq = h->nq;
-        SOLO_REQUIRE(p->tol_mode == SOLO_TOL_DA || p->tol_mode == SOLO_TOL_PPM, SOLO_EINVAL,
-                     "Unknown precursor tolerance mode");
-        SOLO_REQUIRE(p->max_pairs > 0 && p->k >= 1, SOLO_EINVAL, "bad parameters");
-        SOLO_REQUIRE(q_begin >= 0 && nq_slice >= 0 && q_begin + nq_slice <= nq, SOLO_EINVAL, "query slice out of range");
-        if (h->ivf.count(charge) && h->ivf[charge].nlist > 0)
-            SOLO_REQUIRE(h->ivf[charge].ntotal == L.n, SOLO_ESTATE, "ANN index of charge %d holds %lld rows but the library has %lld",
-                         charge, (long long)h->ivf[charge].ntotal, (long long)L.n);
-        if (h->r_nq != nq || h->r_max_pairs != p->max_pairs) ensure_results(h, nq, p->max_pairs);
+        check_slice_call(h, charge, L, p, q_begin, nq_slice);
         if (nq_slice == 0) return;
-        DevBuf &ovf = h->r_ovf, &sel = h->scratch[20], &dpos = h->scratch[23];
-        ovf.ensure(16);
-        SOLO_CUDA(cudaMemsetAsync(ovf.p, 0, 16, h->stream));
+        DevBuf &sel = h->scratch[20];
         sel.ensure((size_t)nq_slice * p->k * sizeof(int32_t));
-        dpos.ensure((size_t)nq * sizeof(int32_t));
         {
             StageTimer t(h, ST_CANDIDATES, 1);
             filter_ids_kernel<<<nq_slice, 256, 0, h->stream>>>(d_I, p->k, h->q_prec_mz.as<double>() + q_begin,
@@ -1542,29 +1577,34 @@ int solo_score_staged_ids(solo_handle *h, int charge, const solo_search_params *
                                                                h->r_n_cand.as<int32_t>() + q_begin);
             SOLO_CUDA(cudaGetLastError());
         }
-        ScoreArgs a;
-        a.q_mz = h->q_mz.as<float>();
-        a.q_int = h->q_int.as<float>();
-        a.q_off = h->q_off.as<int64_t>() + q_begin;  // CSR offsets are absolute: a shifted view is a valid batch
-        a.q_prec_mz = h->q_prec_mz.as<double>() + q_begin;
-        a.nq = nq_slice;
-        a.q_max_peaks = h->q_max_peaks;
-        a.lib = &L;
-        a.tol = p->fragment_mz_tolerance;
-        a.allow_shift = p->allow_shift;
-        a.max_pairs = p->max_pairs;
-        a.best_pos = dpos.as<int32_t>() + q_begin;
-        a.best_row = h->r_best_row.as<int32_t>() + q_begin;
-        a.best_score = h->r_best_score.as<double>() + q_begin;
-        a.n_pairs = h->r_n_pairs.as<int32_t>() + q_begin;
-        a.pairs = h->r_pairs.as<uint32_t>() + (size_t)q_begin * p->max_pairs * 2;
-        a.overflow = ovf.as<int32_t>();
-        a.tie_by_row = 1;
-        a.cand_ids = sel.as<int32_t>();
-        a.cand_off = nullptr;
-        a.cand_cnt = h->r_n_cand.as<int32_t>() + q_begin;
-        a.cand_stride = p->k;
-        launch_best_match(h, a);
+        score_slice(h, L, p, sel.as<int32_t>(), q_begin, nq_slice);
+    });
+}
+
+int solo_merge_score_staged(solo_handle *h, int charge, const solo_search_params *p, const uint64_t *d_parts, int parts,
+                            int slice_len, int q_begin, int nq_slice) {
+    if (!h || !p || !d_parts) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        LibraryStore &L = get_lib(h, charge);
+        IvfIndex &ix = get_ivf(h, charge, true);
+        check_slice_call(h, charge, L, p, q_begin, nq_slice);
+        SOLO_REQUIRE(parts >= 1 && nq_slice <= slice_len, SOLO_EINVAL, "bad merge shape");
+        if (nq_slice == 0) return;
+        DevBuf &sel = h->scratch[20];
+        sel.ensure((size_t)nq_slice * p->k * sizeof(int32_t));
+        IvfSearchArgs win;
+        memset(&win, 0, sizeof win);
+        win.win_q_prec_mz = h->q_prec_mz.as<double>() + q_begin;
+        win.win_lib_prec_mz32 = L.prec_mz32.as<float>();
+        win.win_lib_valid = L.valid.as<uint8_t>();
+        win.win_charge = charge;
+        win.win_tol = p->tol_value;
+        win.win_tol_mode = p->tol_mode;
+        // the fp32 query vectors and their norms were left by solo_ivf_scan_staged (all staged queries)
+        ivf_merge_select(h, ix, reinterpret_cast<const unsigned long long *>(d_parts), parts, slice_len, p->k,
+                         h->scratch[19].as<float>() + (size_t)q_begin * h->hash_len, h->scratch[22].as<float>() + q_begin,
+                         nq_slice, win, sel.as<int32_t>(), h->r_n_cand.as<int32_t>() + q_begin);
+        score_slice(h, L, p, sel.as<int32_t>(), q_begin, nq_slice);
     });
 }
 

@@ -160,6 +160,8 @@ struct IvfIndex {
     bool dirty = true;      // lists need rebuilding before the next search
     int64_t max_list_len = 0;
     int buf_cap = 0;        // per-query candidate buffer capacity used by the scan
+    float last_eps_rel = 0.f;   // error model of the scores the last search produced (the mode-B merge re-uses it)
+    int last_eps_nonneg = 0;
     // TMA descriptor (CUtensorMap, 128 bytes) of vec_h for the tcgen05 scan engine
     alignas(64) unsigned char tmap_storage[128];
     bool tmap_valid = false;

@@ -457,10 +457,21 @@ class SoloEngine:
         self._check(self._lib.solo_ivf_probe_staged(self._h, int(charge), int(nprobe), int(q_begin), int(nq_slice),
                                                     C.c_void_p(d_probes)))
 
-    def ivf_scan_staged(self, charge: int, k: int, nprobe: int, d_probes: int, d_I: int, d_D: int):
-        """Scan this GPU's lists for every staged query with given probe rows d_probes (nq, nprobe) int32."""
+    def ivf_scan_staged(self, charge: int, k: int, nprobe: int, d_probes: int, d_I: int = 0, d_D: int = 0,
+                        d_packed: int = 0):
+        """Scan this GPU's lists for every staged query with given probe rows d_probes (nq, nprobe) int32. Output:
+        sorted d_I / d_D, or d_packed (nq, k) uint64 — the unsorted exchange format of mode B."""
         self._check(self._lib.solo_ivf_scan_staged(self._h, int(charge), int(k), int(nprobe), C.c_void_p(d_probes),
-                                                   C.c_void_p(d_I), C.c_void_p(d_D)))
+                                                   C.c_void_p(d_I or None), C.c_void_p(d_D or None),
+                                                   C.c_void_p(d_packed or None)))
+
+    def merge_score_staged(self, charge: int, params: SearchParams, d_parts: int, parts: int, slice_len: int,
+                           q_begin: int, nq_slice: int):
+        """Mode B, owner of a query slice: exact global top-k out of `parts` packed local top-k tensors
+        (parts, slice_len, k), precursor window, best match — results in rows [q_begin, q_begin + nq_slice)."""
+        self._check(self._lib.solo_merge_score_staged(self._h, int(charge), C.byref(params), C.c_void_p(d_parts),
+                                                      int(parts), int(slice_len), int(q_begin), int(nq_slice)))
+        self._staged_max_pairs = params.max_pairs
 
     def merge_topk_device(self, d_D_parts: int, d_I_parts: int, parts: int, nq: int, k: int, q_begin: int, nq_out: int,
                           d_D: int, d_I: int):

@@ -94,6 +94,9 @@ def allgather_topk(D: np.ndarray, I: np.ndarray, k: int):
     return merge_topk([t.cpu().numpy() for t in gD], [t.cpu().numpy() for t in gI], k)
 
 
+_PACKED_PAD = -0x7FFFFF00000001   # 0xFF800000FFFFFFFF as int64: score -inf, row -1 (solo_b200.h)
+
+
 def slice_bounds(n: int, rank: int, world: int):
     """Mode B query slices: equal length ceil(n / world) (what all_gather_into_tensor / all_to_all_single
     exchange), the last ones clipped at n. Returns (begin, end, slice_len)."""
@@ -110,13 +113,16 @@ def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world
     1. coarse scoring + probe selection by QUERIES: rank r does it for its slice, the (slice, nprobe) int32 rows
        are all-gathered (NCCL over NVLink) — every GPU then knows every query's lists;
     2. the list scan + exact top-k by LISTS: every GPU scans the lists it owns for all queries;
-    3. the per-GPU top-k rows go to the GPU that owns the query slice with ONE all-to-all (rank r receives only
-       its slice's rows from every peer: Q k 12 / world bytes per peer instead of the whole (Q, k) tensor);
-    4. every GPU merges its slice under (score desc, id asc) and finishes it (precursor window, best match).
+    3. the per-GPU top-k entries — unsorted, 8 bytes each: (approximate score, library row) — go to the GPU that
+       owns the query slice with ONE all-to-all (rank r receives only its slice's rows from every peer:
+       Q k 8 / world bytes per peer instead of the whole (Q, k) tensor);
+    4. every GPU selects the exact global top-k of its slice with the single-GPU band rule (entries near the k-th
+       score are re-scored exactly from the sparse rows every GPU keeps) and finishes it (precursor window, best
+       match).
 
     Everything runs on the engine's stream = torch's current stream, so the collectives are ordered behind the
-    kernels without host synchronisation. Returns (results of the slice, (merged D, merged I)); the merged top-k
-    equals the single-GPU top-k bit for bit.
+    kernels without host synchronisation. Returns the results of the slice; the candidate sets, hence the SSMs,
+    equal the single-GPU ones exactly.
 
     ``peers``: single-process variant used by the one-GPU test — a list of engines standing in for the ranks (each
     owning some lists); the exchanges are tensor copies instead of collectives.
@@ -147,30 +153,26 @@ def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world
             dist.all_gather_into_tensor(probes_all, mine, group=group)
         else:
             eng.ivf_probe_staged(charge, nprobe, b, en - b, probes_all.data_ptr())
-    # 2. scan of the owned lists for every query, 3. exchange towards the owner of each query slice
-    recv_D = torch.empty((parts, S, k), dtype=torch.float32, device=dev)
-    recv_I = torch.empty((parts, S, k), dtype=torch.int64, device=dev)
+    # 2. scan of the owned lists for every query, 3. exchange towards the owner of each query slice: packed
+    #    (score bits << 32 | row) entries, 8 bytes each, unsorted
+    recv = torch.empty((parts, S, k), dtype=torch.int64, device=dev)
     my = rank
     for r, e in enumerate(engines):
-        loc_D = torch.full((parts * S, k), float("-inf"), dtype=torch.float32, device=dev)
-        loc_I = torch.full((parts * S, k), -1, dtype=torch.int64, device=dev)
-        e.ivf_scan_staged(charge, k, nprobe, probes_all.data_ptr(), loc_I.data_ptr(), loc_D.data_ptr())
+        loc = torch.empty((parts * S, k), dtype=torch.int64, device=dev)
+        if parts * S > nq:
+            loc[nq:].fill_(_PACKED_PAD)
+        e.ivf_scan_staged(charge, k, nprobe, probes_all.data_ptr(), d_packed=loc.data_ptr())
         if peers is not None:
-            recv_D[r].copy_(loc_D[my * S:(my + 1) * S])
-            recv_I[r].copy_(loc_I[my * S:(my + 1) * S])
+            recv[r].copy_(loc[my * S:(my + 1) * S])
         elif world > 1:
             import torch.distributed as dist
-            dist.all_to_all_single(recv_D.view(parts * S, k), loc_D, group=group)
-            dist.all_to_all_single(recv_I.view(parts * S, k), loc_I, group=group)
+            dist.all_to_all_single(recv.view(parts * S, k), loc, group=group)
         else:
-            recv_D, recv_I = loc_D.view(1, S, k), loc_I.view(1, S, k)
+            recv = loc.view(1, S, k)
     if stats is not None:
-        stats["bytes_sent_per_rank"] = int((parts - 1) * S * (nprobe * 4 + k * 12)) if parts > 1 else 0
-    # 4. merge + finish the slice
+        stats["bytes_sent_per_rank"] = int((parts - 1) * S * (nprobe * 4 + k * 8)) if parts > 1 else 0
+    # 4. exact global top-k of the slice (band re-scored from the replicated sparse rows), window, best match
     b, en, _ = slice_bounds(nq, my, parts)
-    mD = torch.empty((max(en - b, 1), k), dtype=torch.float32, device=dev)
-    mI = torch.empty((max(en - b, 1), k), dtype=torch.int64, device=dev)
-    eng.merge_topk_device(recv_D.data_ptr(), recv_I.data_ptr(), parts, S, k, 0, en - b, mD.data_ptr(), mI.data_ptr())
-    eng.score_staged_ids(charge, params, mI.data_ptr(), b, en - b)
+    eng.merge_score_staged(charge, params, recv.data_ptr(), parts, S, b, en - b)
     res = eng.fetch_results()
-    return {key: v[b:en] for key, v in res.items()}, (mD[:en - b], mI[:en - b])
+    return {key: v[b:en] for key, v in res.items()}

@@ -32,6 +32,18 @@ WORKLOADS = {
                 label="C2 (second point, nlist 4096)"),
     "c1": dict(n_targets=200_000, decoys=0.5, nq=16384, nlist=256, nprobe=128, k=1024, cpu_sample=512,
                label="C1: 16,384 queries vs 200k+100k-decoy library, charges 2-4"),
+    # streamed workloads (run_stream): the whole query set goes through the engine in batches of `nq`, like the
+    # reference's loop over config.batch_size (spectral_library.py:301-306)
+    "c3": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=0,
+               stream_queries=1_048_576, stream_scaling="strong", levels=("open",),
+               label="C3: 1,048,576 queries (ONE set, partitioned over the ranks) vs 3M-vector library, streamed in "
+                     "batches of 16,384 per charge, results gathered to rank 0"),
+    "c4": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=0,
+               stream_queries=1_048_576, stream_scaling="weak", levels=("std", "open"),
+               label="C4 (bounded): 64 batches of 16,384 queries per rank of the 25M-query run vs 3M-vector library, "
+                     "both cascade levels (20 ppm window-only search, then the 500 Da ANN open search) on every query"),
+    "c3s": dict(n_targets=20_000, decoys=0.5, nq=1024, nlist=64, nprobe=16, k=128, cpu_sample=0,
+                stream_queries=10_000, stream_scaling="strong", levels=("std", "open"), label="streamed smoke workload"),
     "tiny": dict(n_targets=20_000, decoys=0.5, nq=1024, nlist=64, nprobe=16, k=128, cpu_sample=256,
                  label="tiny smoke workload"),
 }
@@ -337,6 +349,158 @@ def run_solo(args, wl, rank, world, local_rank):
         sys.exit(1)
 
 
+def run_stream(args, wl, rank, world, local_rank):
+    """C3 / C4: a long query set streamed through SoloEngine.search_stream (copy stream + two query slots). One step =
+    one pass over the whole set: every rank streams its share batch by batch (per charge, `nq` queries per batch)
+    through every cascade level asked for, from pinned host buffers into pinned host results; with N > 1 the results
+    are then gathered to rank 0 over NCCL inside the timed region."""
+    import torch
+    from ann_solo_b200 import parallel, synth
+    from ann_solo_b200.engine import SoloEngine
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_stream(torch.cuda.Stream())
+    t0 = time.time()
+    lib = synth.make_library(wl["n_targets"], decoy_fraction=wl["decoys"], seed=1, decoy_seed=2)
+    per_charge = synth.split_by_charge(lib)
+    strong = wl["stream_scaling"] == "strong"
+    queries = synth.make_queries(lib, wl["stream_queries"], seed=3 if strong else 3 + rank)
+    log(f"synthetic data: {len(lib['prec_mz'])} library spectra, {wl['stream_queries']} queries in {time.time() - t0:.1f}s")
+    eng = SoloEngine(local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    charges = sorted(per_charge)
+    t0 = time.time()
+    for z in charges:
+        store, _ = per_charge[z]
+        eng.load_library(z, store)
+        eng.ivf_train_library(z, min(wl["nlist"], max(1, len(store["prec_mz"]) // 39)), iters=TRAIN_ITERS, seed=4)
+        eng.ivf_add_library(z)
+    eng.synchronize()
+    log(f"index build: {time.time() - t0:.1f}s")
+    del lib
+    max_pairs = 50
+    level_params = {"open": SoloEngine.make_params(True, wl["k"], wl["nprobe"], OPEN_TOL, OPEN_MODE, FRAG_TOL, True, max_pairs),
+                    "std": SoloEngine.make_params(False, wl["k"], wl["nprobe"], 20.0, "ppm", FRAG_TOL, True, max_pairs)}
+    # this rank's share, cut into batches; pinned inputs and outputs
+    pin_keep, batches, h2d_bytes, d2h_bytes, n_local = [], [], 0, 0, 0
+    out_fields = (("best_row", (), np.int32), ("score", (), np.float64), ("n_pairs", (), np.int32),
+                  ("pairs", (max_pairs, 2), np.uint32), ("n_cand", (), np.int32))
+    for z in charges:
+        rows = np.flatnonzero(queries["prec_z"] == z)
+        if strong:
+            b, e = parallel.shard_bounds(len(rows), rank, world)
+            rows = rows[b:e]
+        for b0 in range(0, len(rows), wl["nq"]):
+            q = synth.take_spectra(queries, rows[b0:b0 + wl["nq"]])
+            hq = {}
+            for key in ("mz", "inten", "off", "prec_mz"):
+                t, hq[key] = pinned_copy(torch, q[key])
+                pin_keep.append(t)
+                h2d_bytes += hq[key].nbytes
+            n = len(q["prec_mz"])
+            out = {}
+            for key, tail, dt in out_fields:
+                t = torch.empty((n,) + tail, dtype=getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))).pin_memory()
+                pin_keep.append(t)
+                out[key] = t.numpy().view(dt)
+                d2h_bytes += out[key].nbytes
+            batches.append((z, hq, out))
+            n_local += n
+    del queries
+    levels = wl["levels"]
+    n_max = n_local
+    if dist is not None:
+        t = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_max = int(t.item())
+    gathered = {}
+
+    def one_pass(sel=None):
+        todo = batches if sel is None else batches[:sel]
+        for lv in levels:
+            for _ in eng.search_stream(level_params[lv], todo):
+                pass
+        if dist is None or sel is not None:
+            return
+        # results of the (last) level to rank 0: one padded device tensor per field
+        for key, tail, dt in out_fields:
+            tdt = getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))
+            loc = torch.zeros((n_max,) + tail, dtype=tdt, device="cuda")
+            host = np.concatenate([o[key] for _, _, o in batches]) if batches else np.zeros((0,) + tail, dt)
+            loc[:len(host)].copy_(torch.from_numpy(host.view(np.dtype(dt).name.replace("uint32", "int32"))), non_blocking=True)
+            parts = [torch.empty_like(loc) for _ in range(world)] if rank == 0 else None
+            dist.gather(loc, parts, dst=0)
+            if rank == 0:
+                gathered[key] = torch.stack(parts).cpu()
+
+    one_pass(sel=min(6, len(batches)))     # warm-up on a few batches of the stream (buffers, slots, lazy module loads)
+    for _ in range(max(0, args.warmup - 1)):
+        one_pass(sel=min(6, len(batches)))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        eng.profile_reset()
+        eng.profile_enable(True)
+        l0 = eng.kernel_launches()
+        e0.record()
+        for _ in range(args.steps):
+            one_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+    prof = eng.profile()
+    eng.profile_enable(False)
+    launches = eng.kernel_launches() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([n_local, sum(int((o["best_row"] >= 0).sum()) for _, _, o in batches)], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    if rank != 0:
+        return
+    ms = float(ms.item())
+    n_all, n_match = int(tot[0].item()), int(tot[1].item())
+    assert n_match > 0.5 * n_all, f"only {n_match} of {n_all} queries matched"
+    if gathered:
+        assert int((gathered["best_row"] >= 0).sum()) == n_match, "gathered results differ from the ranks' own counts"
+    value = n_all * args.steps / (ms / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    scan = prof["scan"]
+    achieved = scan["units"] / (scan["ms"] * 1e-3) / 1e12 if scan["ms"] > 0 else 0.0
+    _emit(json.dumps({
+        "metric": "query spectra/sec, cascade open search", "value": round(value, 1), "unit": "spectra/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": wl["stream_scaling"], "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "queries_per_step": n_all, "batch": wl["nq"], "batches_rank0": len(batches),
+                   "cascade_levels": list(levels), "nlist": wl["nlist"], "nprobe": wl["nprobe"], "k": wl["k"],
+                   "parallelism": f"queries partitioned x{world}, library replicated" +
+                                  (", results gathered to rank 0 (NCCL) inside the timed region" if world > 1 else ""),
+                   "l2": "index and peak store (>1 GB) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": round(value, 1), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d_bytes * len(levels)),
+                "d2h_bytes_per_step": int(d2h_bytes * len(levels)),
+                "note": "the streamed run IS the end-to-end path: pinned host buffers in, pinned host results out, copies on "
+                        "the copy stream under the kernels"},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": {"kernel": "k3_list_scan", "bound": "tensor", "achieved": round(achieved, 3), "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 5), "traffic": None,
+                     "share_of_step": round(scan["ms"] / ms, 4)},
+        "stage_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["ms"] > 0},
+        "matched_queries": n_match, "cpu_baseline": None,
+    }))
+
+
 def measure_extras(eng, charges, q_by_charge, nq_rank, torch):
     """--extras: the widened rows of SURVEY.md §8f next to the hot path, on the same resident data.
     N4: K6 SSM feature table for the SSMs the last step produced (every charge), through the C-ABI with
@@ -417,7 +581,7 @@ def measure_sharded(args, wl, rank, world, eng, charges, lib, params, torch, dis
     def step():
         sent = 0
         for z in charges:
-            res, _ = parallel.search_batch_sharded(eng, z, params, q_by_charge[z], rank, world, stats=stats)
+            res = parallel.search_batch_sharded(eng, z, params, q_by_charge[z], rank, world, stats=stats)
             last[z] = res
             sent += stats.get("bytes_sent_per_rank", 0)
         return sent
@@ -461,7 +625,7 @@ def measure_sharded(args, wl, rank, world, eng, charges, lib, params, torch, dis
     return {"value": round(nq_total * args.steps / (ms / 1e3), 1), "unit": "spectra/s", "ms_per_step": round(ms / args.steps, 3),
             "scaling": "strong", "global_batch": nq_total, "matched_queries": int(m.item()),
             "bytes_sent_per_rank_per_step": int(sent),
-            "exchange": "all-gather of probe rows (int32) + all-to-all of top-k rows (f32 score, i64 id) over NCCL",
+            "exchange": "all-gather of probe rows (int32) + all-to-all of packed top-k entries (f32 score | u32 row) over NCCL",
             "stage_ms_per_step_rank0": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0},
             "mismatch_vs_replicated": mismatch,
             "note": "inverted lists sharded x%d; host query buffers staged and the slice's results fetched every step" % world}
@@ -643,6 +807,8 @@ def main():
         os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
+    elif "stream_queries" in wl:
+        run_stream(args, wl, rank, world, local_rank)
     else:
         run_solo(args, wl, rank, world, local_rank)
 

@@ -319,7 +319,15 @@ int solo_ivf_search_staged(solo_handle *h, int charge, int k, int nprobe, int64_
  * d_probes (nq, nprobe) and leaves the local top-k like solo_ivf_search_staged. */
 int solo_ivf_probe_staged(solo_handle *h, int charge, int nprobe, int q_begin, int nq_slice, int32_t *d_probes);
 int solo_ivf_scan_staged(solo_handle *h, int charge, int k, int nprobe, const int32_t *d_probes, int64_t *d_I,
-                         float *d_D);
+                         float *d_D, uint64_t *d_packed);
+/* d_packed (nq, k) uint64 instead of d_I / d_D: the exchange format — (float32 score bits << 32 | library row),
+ * unsorted, padded with 0xFF800000FFFFFFFF; certain members of the local top-k carry their approximate score, band
+ * members their exact one. solo_merge_score_staged takes `parts` such tensors laid out (parts, slice_len, k) — what an
+ * all-to-all leaves on the owner of the query slice [q_begin, q_begin + nq_slice) —, selects the exact global top-k
+ * (same band rule as the single-GPU path, re-scoring from the sparse rows every GPU keeps), applies the precursor
+ * window AND valid, and runs the best match; results land in the rows [q_begin, ...) of solo_fetch_results. */
+int solo_merge_score_staged(solo_handle *h, int charge, const solo_search_params *p, const uint64_t *d_parts, int parts,
+                            int slice_len, int q_begin, int nq_slice);
 /* Merge `parts` such results, laid out (parts, nq, k) as all_gather_into_tensor leaves them, for the
  * queries [q_begin, q_begin + nq_out): d_D/d_I (nq_out, k), same order and padding. */
 int solo_merge_topk_device(solo_handle *h, const float *d_D_parts, const int64_t *d_I_parts, int parts, int nq, int k,

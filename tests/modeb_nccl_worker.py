@@ -31,17 +31,14 @@ def main():
     eng.ivf_add_library(charge)
     params = SoloEngine.make_params(True, k, nprobe, 500.0, "Da", 0.02, True, max_pairs=64)
     ref = {key: v.copy() for key, v in eng.search_batch(charge, params, q).items()}
-    D_ref, I_ref = eng.ivf_search(charge, eng.vectorize(q["mz"], q["inten"], q["off"]), k, nprobe)
     assign = eng.ivf_assignment(charge)
     owner = parallel.assign_lists(np.bincount(assign[assign >= 0], minlength=nlist), world)
     eng.ivf_set_owned_lists(charge, (owner == rank).astype(np.uint8))
     bad = 0
     for rep in range(2):   # twice: buffers and streams are reused across batches
         stats = {}
-        res, (mD, mI) = parallel.search_batch_sharded(eng, charge, params, q, rank, world, stats=stats)
+        res = parallel.search_batch_sharded(eng, charge, params, q, rank, world, stats=stats)
         b, e, _ = parallel.slice_bounds(nq, rank, world)
-        bad += int(not np.array_equal(mI.cpu().numpy(), I_ref[b:e]))
-        bad += int(not np.array_equal(mD.cpu().numpy().view(np.uint32), D_ref[b:e].view(np.uint32)))
         for key in ("best_row", "n_pairs", "n_cand"):
             bad += int(not np.array_equal(res[key], ref[key][b:e]))
         bad += int(not np.array_equal(res["score"].view(np.uint64), ref["score"][b:e].view(np.uint64)))

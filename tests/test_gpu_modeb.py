@@ -43,12 +43,26 @@ def test_sharded_lists_equal_single_gpu(engine, oracle, synth, world):
         peers.append(e)
     got = {}
     for r in range(world):  # every "rank" merges and finishes its own slice of the queries
-        res, (mD, mI) = parallel.search_batch_sharded(peers[r], charge, params, q, rank=r, world=world, peers=peers)
-        b, e_, _ = parallel.slice_bounds(nq, r, world)
-        assert np.array_equal(mI.cpu().numpy(), I_ref[b:e_]), "merged ids differ from the single-GPU top-k"
-        assert np.array_equal(mD.cpu().numpy().view(np.uint32), D_ref[b:e_].view(np.uint32))
+        res = parallel.search_batch_sharded(peers[r], charge, params, q, rank=r, world=world, peers=peers)
         for key, v in res.items():
             got.setdefault(key, []).append(v)
+    # the sorted (D, I) form of the local search still merges to the single-GPU top-k bit for bit
+    dev = torch.device("cuda", 0)
+    pr = torch.empty((nq, nprobe), dtype=torch.int32, device=dev)
+    peers[0].stage_queries(q)
+    peers[0].ivf_probe_staged(charge, nprobe, 0, nq, pr.data_ptr())
+    aD = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+    aI = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+    for r in range(world):
+        peers[r].stage_queries(q)
+        peers[r].ivf_scan_staged(charge, k, nprobe, pr.data_ptr(), aI[r].data_ptr(), aD[r].data_ptr())
+        peers[r].synchronize()
+    mD = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    mI = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    peers[0].merge_topk_device(aD.data_ptr(), aI.data_ptr(), world, nq, k, 0, nq, mD.data_ptr(), mI.data_ptr())
+    peers[0].synchronize()
+    assert np.array_equal(mI.cpu().numpy(), I_ref), "merged ids differ from the single-GPU top-k"
+    assert np.array_equal(mD.cpu().numpy().view(np.uint32), D_ref.view(np.uint32))
     for key in ("best_row", "score", "n_pairs", "n_cand"):
         assert np.array_equal(np.concatenate(got[key]), ref[key]), key
     pairs = np.concatenate(got["pairs"])
