@@ -84,6 +84,7 @@ SYMBOLS = {
     "solo_stage_queries": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "solo_search_staged": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams)]),
     "solo_fetch_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "solo_fetch_results_range": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "solo_search_batch": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp, _vp, _vp, _vp]),
     "solo_stage_queries_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),

@@ -991,6 +991,33 @@ int solo_fetch_results(solo_handle *h, int32_t *best_row, double *best_score, in
     });
 }
 
+int solo_fetch_results_range(solo_handle *h, int q_begin, int n, int32_t *best_row, double *best_score, int32_t *n_pairs,
+                             uint32_t *pairs, int32_t *n_cand) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(q_begin >= 0 && n >= 0 && q_begin + n <= h->r_nq, SOLO_EINVAL, "result rows [%d, %d) out of range (%d staged)",
+                     q_begin, q_begin + n, h->r_nq);
+        if (n == 0) return;
+        int32_t n_over = 0;
+        const size_t mp = (size_t)h->r_max_pairs;
+        {
+            StageTimer t(h, ST_D2H, 0, (double)n * (4 + 8 + 4 + 4 + (double)mp * 8));
+            auto cp = [&](void *dst, const DevBuf &src, size_t elem) {
+                if (dst) SOLO_CUDA(cudaMemcpyAsync(dst, src.as<unsigned char>() + (size_t)q_begin * elem, (size_t)n * elem,
+                                                   cudaMemcpyDeviceToHost, h->stream));
+            };
+            cp(best_row, h->r_best_row, 4);
+            cp(best_score, h->r_best_score, 8);
+            cp(n_pairs, h->r_n_pairs, 4);
+            cp(pairs, h->r_pairs, mp * 8);
+            cp(n_cand, h->r_n_cand, 4);
+            SOLO_CUDA(cudaMemcpyAsync(&n_over, h->r_ovf.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+        SOLO_CUDA(cudaStreamSynchronize(h->stream));
+        h->k5_overflow_pairs += n_over;
+    });
+}
+
 int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, const float *q_mz, const void *q_mz_vec,
                       const float *q_intensity, const int64_t *q_off, const double *q_prec_mz, int nq,
                       int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs, int32_t *n_cand) {

@@ -278,6 +278,15 @@ class SoloEngine:
                                                  _ptr(out["n_pairs"]), _ptr(out["pairs"]), _ptr(out["n_cand"])))
         return out
 
+    def fetch_results_range(self, q_begin: int, n: int) -> dict:
+        """Result rows [q_begin, q_begin + n) of the staged batch."""
+        mp = self._staged_max_pairs
+        out = dict(best_row=np.empty(n, np.int32), score=np.empty(n, np.float64), n_pairs=np.empty(n, np.int32),
+                   pairs=np.empty((n, mp, 2), np.uint32), n_cand=np.empty(n, np.int32))
+        self._check(self._lib.solo_fetch_results_range(self._h, int(q_begin), int(n), _ptr(out["best_row"]), _ptr(out["score"]),
+                                                       _ptr(out["n_pairs"]), _ptr(out["pairs"]), _ptr(out["n_cand"])))
+        return out
+
     def search_batch(self, charge: int, params: SearchParams, q: dict, mz_vec: Optional[np.ndarray] = None,
                      out: Optional[dict] = None) -> dict:
         """One batch through the whole hot path with host buffers (vectorise -> IVF top-k ->

@@ -138,6 +138,9 @@ def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world
     for e in engines:
         e.set_stream(stream)
         e.stage_queries(q, mz_vec)
+        # the unconditional first scan round seeds the running threshold from the closest OWNED lists: with the
+        # lists dealt over `parts` GPUs a proportionally smaller round gives the same coverage of the probe ranking
+        e.set_option("round0_scores", min(16384, max(1024, 2 * k, 4096 // parts)))
     # 1. probes, sharded by queries
     probes_all = torch.zeros((parts * S, nprobe), dtype=torch.int32, device=dev)
     if peers is not None:
@@ -174,5 +177,7 @@ def search_batch_sharded(eng, charge: int, params, q: dict, rank: int = 0, world
     # 4. exact global top-k of the slice (band re-scored from the replicated sparse rows), window, best match
     b, en, _ = slice_bounds(nq, my, parts)
     eng.merge_score_staged(charge, params, recv.data_ptr(), parts, S, b, en - b)
-    res = eng.fetch_results()
-    return {key: v[b:en] for key, v in res.items()}
+    res = eng.fetch_results_range(b, en - b)
+    for e in engines:
+        e.set_option("round0_scores", 4096)   # the single-GPU default
+    return res

@@ -282,7 +282,9 @@ def run_solo(args, wl, rank, world, local_rank):
                 pc = np.percentile(cnt, [1, 50, 90, 99, 100]).astype(int).tolist()
                 log(f"   z={z}: scan-buffer entries/query p1/p50/p90/p99/max = {pc} mean={cnt.mean():.0f}")
     ms_res, prof, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), streamed=True)
+    ms_e2e, prof_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), profile=True, streamed=True)
+    log("e2e stages (ms/step): " + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof_e2e.items() if v["ms"] > 0))
+    log("resident stages (ms/step): " + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof.items() if v["ms"] > 0))
     value = world * nq_rank * args.steps / (ms_res / 1e3)
     e2e = world * nq_rank * args.steps / (ms_e2e / 1e3)
 

@@ -189,6 +189,9 @@ int solo_search_staged(solo_handle *h, int charge, const solo_search_params *p);
  * best_row: library row of the winner (-1 = no candidate); n_cand: candidates scored. */
 int solo_fetch_results(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs,
                        uint32_t *pairs, int32_t *n_cand);
+/* solo_fetch_results for the result rows [q_begin, q_begin + n) only (mode B: a GPU finishes one slice of the batch). */
+int solo_fetch_results_range(solo_handle *h, int q_begin, int n, int32_t *best_row, double *best_score, int32_t *n_pairs,
+                             uint32_t *pairs, int32_t *n_cand);
 /* stage + search + fetch. */
 int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, const float *q_mz,
                       const void *q_mz_vec, const float *q_intensity, const int64_t *q_off,
