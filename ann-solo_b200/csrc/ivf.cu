@@ -389,13 +389,12 @@ struct SelectArgs {
     int n_front;                      // fast path: roughly the n_front best lists are written first
 };
 
-__global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a) {
+__device__ void select_probes_one(const SelectArgs &a, const int q) {
     extern __shared__ __align__(16) uint32_t s_sel_keys[];  // [nlist]
     uint32_t *s_keys = s_sel_keys;
     __shared__ uint32_t s_hist[KTH_BINS];
     __shared__ uint32_t s_bc[KTH_BC];
     __shared__ int s_cnt, s_eq_taken, s_back;
-    const int q = blockIdx.x;
     const int nlist = a.nlist, nprobe = a.nprobe;
     int32_t *probes = a.probes;
     unsigned long long *probe_keys = a.probe_keys;
@@ -557,6 +556,142 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a
             s_eq_taken += tot;
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_probes_kernel(SelectArgs a) { select_probes_one(a, blockIdx.x); }
+
+// the same for the queries of a device-side list (the compact path's fall-back): a few persistent CTAs
+__global__ void __launch_bounds__(SEL_THREADS)
+select_probes_listed_kernel(SelectArgs a, const int32_t *__restrict__ qlist, const int32_t *__restrict__ n_listed) {
+    const int n = *n_listed;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        select_probes_one(a, qlist[i]);
+        __syncthreads();
+    }
+}
+
+// ---- compact probe selection: the coarse pass kept only scores >= tau[q] (a quantile estimated on a sample of the
+// centroids), so a query's candidates are a few thousand (score, list) pairs instead of a dense row of nlist scores.
+
+// tau[q] = the m-th largest of the query's scores against the first `ns` centroids (a random sample: k-means
+// starts from randomly drawn rows)
+__global__ void __launch_bounds__(128)
+coarse_tau_kernel(const float *__restrict__ sample, int ld, int ns, int m, float *__restrict__ tau,
+                  int32_t *__restrict__ ccnt, int32_t *__restrict__ n_fail) {
+    extern __shared__ uint32_t s_tau_keys[];
+    __shared__ uint32_t s_hist[KTH_BINS];
+    __shared__ uint32_t s_bc[KTH_BC];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const float v = sample[(int64_t)q * ld + i];
+        s_tau_keys[i] = (v == v) ? ivf_f2o(v) : 0u;
+    }
+    if (q == 0 && threadIdx.x == 0) *n_fail = 0;
+    __syncthreads();
+    int gt;
+    const uint32_t T = block_kth_largest_u32(s_tau_keys, ns, m, false, 0u, s_hist, s_bc, &gt);
+    if (threadIdx.x == 0) {
+        tau[q] = ivf_o2f(T);
+        ccnt[q] = 0;
+    }
+}
+
+struct CompactSelectArgs {
+    const unsigned long long *cbuf;   // (nq, cap) (score bits << 32 | list)
+    const int32_t *ccnt;
+    const float *tau;
+    int cap;
+    int32_t *fail_list;               // queries that must go through the dense path
+    int32_t *n_fail;
+    SelectArgs s;                     // probes, eps, sparse queries, centroids, n_front
+};
+
+__global__ void __launch_bounds__(256) select_probes_compact_kernel(CompactSelectArgs ca) {
+    extern __shared__ __align__(16) uint32_t s_ckeys[];  // [cap] keys, then [cap] list ids
+    const SelectArgs &a = ca.s;
+    uint32_t *s_keys = s_ckeys, *s_ids = s_ckeys + ca.cap;
+    __shared__ uint32_t s_hist[KTH_BINS];
+    __shared__ uint32_t s_bc[KTH_BC];
+    __shared__ int s_cnt, s_back, s_nband;
+    __shared__ uint32_t s_band_id[SEL_BCAP];
+    __shared__ unsigned long long s_band_key[SEL_BCAP];
+    const int q = blockIdx.x;
+    const int nprobe = a.nprobe;
+    const int n = ca.ccnt[q];
+    auto fail = [&]() {
+        if (threadIdx.x == 0) ca.fail_list[atomicAdd(ca.n_fail, 1)] = q;
+    };
+    if (n < nprobe || n > ca.cap) {   // the sampled threshold was too tight (or far too loose)
+        fail();
+        return;
+    }
+    const unsigned long long *row = ca.cbuf + (int64_t)q * ca.cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long e = row[i];
+        s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(e >> 32)));
+        s_ids[i] = (uint32_t)(e & 0xFFFFFFFFull);
+    }
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_back = 0;
+        s_nband = 0;
+    }
+    __syncthreads();
+    int gt;
+    uint32_t fkey = 0u;
+    const uint32_t T = block_kth_largest_u32(s_keys, n, nprobe, false, 0u, s_hist, s_bc, &gt, min(a.n_front, nprobe), &fkey);
+    const float t = ivf_o2f(T);
+    const float e2 = 2.f * band_eps(a.eps, t, q);
+    const float lo = t - e2, hi = t + e2;
+    if (!(lo >= ca.tau[q])) {         // part of the band may lie below the coarse pass's threshold
+        fail();
+        return;
+    }
+    int32_t *probes = a.probes + (int64_t)q * nprobe;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t k0 = s_keys[i];
+        const float s = ivf_o2f(k0);
+        if (s > hi) {   // front: close lists first (they seed the scan's running threshold)
+            const int slot = (a.n_front <= 0 || k0 >= fkey) ? atomicAdd(&s_cnt, 1) : nprobe - 1 - atomicAdd(&s_back, 1);
+            probes[slot] = (int32_t)s_ids[i];
+        } else if (s >= lo) {
+            const int pos = atomicAdd(&s_nband, 1);
+            if (pos < SEL_BCAP) s_band_id[pos] = s_ids[i];
+        }
+    }
+    __syncthreads();
+    const int nband = s_nband, certain = s_cnt + s_back;
+    if (nband > SEL_BCAP) {
+        fail();
+        return;
+    }
+    // the band is re-scored exactly (the oracle's sequential fmaf over the query's non-zeros) and ranked under
+    // (exact score desc, list id asc)
+    const int64_t qb = a.q_off[q], qe = a.q_off[q + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < nband; b += nwarps) {
+        const uint32_t i = s_band_id[b];
+        const float *c = a.cent + (int64_t)i * a.d;
+        float acc = 0.f;
+        for (int64_t e0 = qb; e0 < qe; e0 += 32) {
+            const int64_t e = e0 + lane;
+            const float v = e < qe ? a.q_val[e] : 0.f;
+            const float cv = e < qe ? c[a.q_idx[e]] : 0.f;
+            const int cnt = (int)min((int64_t)32, qe - e0);
+            for (int u = 0; u < cnt; ++u)
+                acc = __fmaf_rn(__shfl_sync(0xffffffffu, v, u), __shfl_sync(0xffffffffu, cv, u), acc);
+        }
+        if (lane == 0)
+            s_band_key[b] = ((unsigned long long)((acc == acc) ? ivf_f2o(acc) : 0u) << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+    }
+    __syncthreads();
+    const int need = nprobe - certain;
+    for (int b = threadIdx.x; b < nband; b += blockDim.x) {
+        const unsigned long long key = s_band_key[b];
+        int r = 0;
+        for (int b2 = 0; b2 < nband; ++b2) r += s_band_key[b2] > key;
+        if (r < need) probes[nprobe - 1 - atomicAdd(&s_back, 1)] = (int32_t)s_band_id[b];
     }
 }
 
@@ -1334,58 +1469,112 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         d_probes_c = d_probes;
         DevBuf &coarse = h->scratch[7];
         const int pitch = (nlist + 31) & ~31;
-        coarse.ensure((size_t)nq * pitch * sizeof(float));
-        {
-            StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
-            if (use_tc_coarse)
-                launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, coarse.as<float>(), pitch);
-            else
-                launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
-                                 coarse.as<float>(), nullptr, pitch);
+        SelectArgs sel;
+        memset(&sel, 0, sizeof sel);
+        sel.pitch = pitch;
+        sel.nlist = nlist;
+        sel.nprobe = nprobe;
+        sel.probes = a.sort_probes ? nullptr : d_probes;
+        sel.eps = ea;
+        if (use_tc_coarse) {
+            sel.eps.rel = IVF_REL_EPS;
+            sel.eps.nonneg = (ix.cent_nonneg && q_nonneg) ? 1 : 0;
+            sel.eps.max_norm = ix.cent_max_norm;
         }
-        {
-            StageTimer t(h, ST_PROBE_SELECT, 1 + (a.sort_probes ? 1 : 0));
-            size_t smem = (size_t)nlist * sizeof(uint32_t);
-            SOLO_CUDA(cudaFuncSetAttribute(select_probes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            unsigned long long *d_keys = nullptr;
-            if (a.sort_probes) {
-                pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
-                d_keys = pkeys.as<unsigned long long>();
-            }
-            SelectArgs sel;
-            memset(&sel, 0, sizeof sel);
-            sel.scores = coarse.as<float>();
-            sel.pitch = pitch;
-            sel.nlist = nlist;
-            sel.nprobe = nprobe;
-            sel.probes = a.sort_probes ? nullptr : d_probes;
-            sel.probe_keys = d_keys;
-            sel.eps = ea;
-            if (use_tc_coarse) {
-                sel.eps.rel = IVF_REL_EPS;
-                sel.eps.nonneg = (ix.cent_nonneg && q_nonneg) ? 1 : 0;
-                sel.eps.max_norm = ix.cent_max_norm;
-            }
-            sel.exact_all = a.sort_probes ? 1 : 0;
-            sel.q_off = q_off.as<int64_t>();
-            sel.q_idx = q_idx.as<uint16_t>();
-            sel.q_val = q_val.as<float>();
-            sel.cent = ix.cent.as<float>();
-            sel.d = d;
-            // lists that fit the unconditional first scan round (c0 scores, see below), with some slack
-            sel.n_front = (ix.nstored > 0 && h->opt_front_probes)
-                              ? (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, 3 * (int64_t)h->opt_round0_scores * nlist / (4 * ix.nstored)))
-                              : 0;
-            select_probes_kernel<<<nq, SEL_THREADS, smem, st>>>(sel);
-            SOLO_CUDA(cudaGetLastError());
-            if (a.sort_probes) {
-                SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
-                int npad = 1;
-                while (npad < nprobe) npad <<= 1;
-                size_t sm2 = (size_t)npad * sizeof(unsigned long long);
-                SOLO_CUDA(cudaFuncSetAttribute(sort_probe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-                sort_probe_rows_kernel<<<nq, 512, sm2, st>>>(d_keys, nprobe, npad, d_probes);
+        sel.exact_all = a.sort_probes ? 1 : 0;
+        sel.q_off = q_off.as<int64_t>();
+        sel.q_idx = q_idx.as<uint16_t>();
+        sel.q_val = q_val.as<float>();
+        sel.cent = ix.cent.as<float>();
+        sel.d = d;
+        // lists that fit the unconditional first scan round (c0 scores, see below), with some slack
+        sel.n_front = (ix.nstored > 0 && h->opt_front_probes)
+                          ? (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, 3 * (int64_t)h->opt_round0_scores * nlist / (4 * ix.nstored)))
+                          : 0;
+        const size_t sel_smem = (size_t)nlist * sizeof(uint32_t);
+        SOLO_CUDA(cudaFuncSetAttribute(select_probes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        // ---- compact path: no (Q, nlist) score matrix. A per-query threshold is estimated on a sample of the
+        // centroids (the first NS: k-means starts from randomly drawn rows) so that about 1.75 nprobe scores pass;
+        // the coarse pass keeps only those, the selection works on a few thousand pairs. A query whose threshold
+        // turned out too tight (or whose band reaches below it) goes through the dense path, decided on the device.
+        constexpr int NS = 512;
+        const double expect = 1.75 * nprobe;
+        const int m_rank = (int)std::ceil(NS * expect / nlist);
+        int cap_c = 1024;
+        while (cap_c < 2.2 * expect) cap_c <<= 1;
+        static const bool env_dense = getenv("SOLO_COARSE_DENSE") != nullptr;
+        const bool compact = use_tc_coarse && !a.sort_probes && !env_dense && h->opt_compact_probes && nlist >= 4 * NS &&
+                             expect <= 0.5 * nlist && m_rank >= 16 && cap_c <= 8192;
+        if (compact) {
+            DevBuf &samp = h->scratch[29], &cbuf = h->scratch[30], &cmisc = h->scratch[31];
+            samp.ensure((size_t)nq * NS * sizeof(float));
+            cbuf.ensure((size_t)nq * cap_c * sizeof(unsigned long long));
+            cmisc.ensure(((size_t)3 * nq + 4) * sizeof(int32_t));
+            float *c_tau = cmisc.as<float>();
+            int32_t *c_cnt = cmisc.as<int32_t>() + nq, *c_fail = cmisc.as<int32_t>() + 2 * (size_t)nq;
+            int32_t *c_nfail = cmisc.as<int32_t>() + 3 * (size_t)nq;
+            {
+                StageTimer t(h, ST_COARSE, 3, 2.0 * nq * (double)nlist * d);
+                launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, samp.as<float>(), NS, NS);
+                coarse_tau_kernel<<<nq, 128, NS * sizeof(uint32_t), st>>>(samp.as<float>(), NS, NS, m_rank, c_tau, c_cnt, c_nfail);
                 SOLO_CUDA(cudaGetLastError());
+                launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, nullptr, 0, -1, c_tau,
+                                 cbuf.as<unsigned long long>(), c_cnt, cap_c);
+            }
+            {
+                StageTimer t(h, ST_PROBE_SELECT, 4);
+                CompactSelectArgs ca;
+                ca.cbuf = cbuf.as<unsigned long long>();
+                ca.ccnt = c_cnt;
+                ca.tau = c_tau;
+                ca.cap = cap_c;
+                ca.fail_list = c_fail;
+                ca.n_fail = c_nfail;
+                ca.s = sel;
+                const size_t csm = (size_t)cap_c * 2 * sizeof(uint32_t);
+                SOLO_CUDA(cudaFuncSetAttribute(select_probes_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+                select_probes_compact_kernel<<<nq, 256, csm, st>>>(ca);
+                SOLO_CUDA(cudaGetLastError());
+                // fall-back for the listed queries (usually none or a handful): dense rows + the dense selection
+                coarse.ensure((size_t)nq * pitch * sizeof(float));
+                launch_coarse_tc_listed(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), q_scale_log2, coarse.as<float>(), pitch,
+                                        c_fail, c_nfail);
+                sel.scores = coarse.as<float>();
+                SOLO_CUDA(cudaFuncSetAttribute(select_probes_listed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+                select_probes_listed_kernel<<<std::min(nq, 2 * kNumSMs), SEL_THREADS, sel_smem, st>>>(sel, c_fail, c_nfail);
+                SOLO_CUDA(cudaGetLastError());
+                h->compact_probe_batches++;
+            }
+        } else {
+            coarse.ensure((size_t)nq * pitch * sizeof(float));
+            {
+                StageTimer t(h, ST_COARSE, 1, 2.0 * nq * (double)nlist * d);
+                if (use_tc_coarse)
+                    launch_coarse_tc(h, ix, qh.as<__half>(), qmask.as<uint32_t>(), nq, q_scale_log2, coarse.as<float>(), pitch);
+                else
+                    launch_coarse<0>(h, ix, q_off.as<int64_t>(), q_idx.as<uint16_t>(), q_val.as<float>(), 0, nq,
+                                     coarse.as<float>(), nullptr, pitch);
+            }
+            {
+                StageTimer t(h, ST_PROBE_SELECT, 1 + (a.sort_probes ? 1 : 0));
+                unsigned long long *d_keys = nullptr;
+                if (a.sort_probes) {
+                    pkeys.ensure((size_t)nq * nprobe * sizeof(unsigned long long));
+                    d_keys = pkeys.as<unsigned long long>();
+                }
+                sel.scores = coarse.as<float>();
+                sel.probe_keys = d_keys;
+                select_probes_kernel<<<nq, SEL_THREADS, sel_smem, st>>>(sel);
+                SOLO_CUDA(cudaGetLastError());
+                if (a.sort_probes) {
+                    SOLO_REQUIRE(nprobe <= 4096, SOLO_ECAPACITY, "sorted probe output supports nprobe <= 4096");
+                    int npad = 1;
+                    while (npad < nprobe) npad <<= 1;
+                    size_t sm2 = (size_t)npad * sizeof(unsigned long long);
+                    SOLO_CUDA(cudaFuncSetAttribute(sort_probe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+                    sort_probe_rows_kernel<<<nq, 512, sm2, st>>>(d_keys, nprobe, npad, d_probes);
+                    SOLO_CUDA(cudaGetLastError());
+                }
             }
         }
     }

@@ -35,6 +35,15 @@ __host__ __device__ __forceinline__ float ivf_o2f(uint32_t u) {
 
 struct IvfSearchScratch;
 
+// One work item of the tcgen05 scan = one chunk of <= NB consecutive vectors of an inverted list, scored against
+// the list's whole query group of this round.
+struct __align__(16) TcItem {
+    int32_t p0;   // first list position of the chunk
+    int32_t nv;   // vectors in the chunk (1..NB)
+    int32_t g0;   // offset of the list's query group in gq
+    int32_t G;    // queries in the group
+};
+
 // Everything the search needs, all device pointers.
 struct IvfSearchArgs {
     const float *q;      // (nq, dim) fp32 query vectors
@@ -67,7 +76,10 @@ bool tc_scan_supported(const IvfIndex &ix);
 void tc_make_tensor_map(IvfIndex &ix);
 void tc_make_centroid_map(IvfIndex &ix);
 void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int nq, int q_scale_log2,
-                      float *out, int ld);
+                      float *out, int ld, int n_lists = -1, const float *tau = nullptr, unsigned long long *buf = nullptr,
+                      int32_t *cnt = nullptr, int cap = 0);
+void launch_coarse_tc_listed(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int q_scale_log2,
+                             float *out, int ld, const int32_t *q_list, const int32_t *n_listed);
 void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int nq, int q_scale_log2, __half *qh,
                         uint32_t *qmask);
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,

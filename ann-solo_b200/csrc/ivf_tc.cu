@@ -147,14 +147,6 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-// One work item = one chunk of <= NB consecutive vectors of an inverted list, scored against the
-// list's whole query group of this round.
-struct __align__(16) TcItem {
-    int32_t p0;   // first list position of the chunk
-    int32_t nv;   // vectors in the chunk (1..NB)
-    int32_t g0;   // offset of the list's query group in gq
-    int32_t G;    // queries in the group
-};
 
 struct TcScanArgs {
     const TcItem *items;
@@ -246,9 +238,11 @@ struct TileCursor {
 // centroid table, the query group is every query).
 // NUM_KB > 0 fixes the number of k-blocks at compile time (dim 800 -> 13) so that the gather loop
 // unrolls into copies with immediate offsets; NUM_KB == 0 is the generic kernel.
+// FLAGS & 4: the query group of every item is the identity (coarse quantizer): an A tile is 128 CONSECUTIVE rows
+// of the fp16 query matrix and comes in by TMA (tmap_q, one box per k-block) instead of the 16-byte gather.
 template <int MODE, int NUM_KB, int EPI, int FLAGS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_constant__ CUtensorMap tmap_q, TcScanArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base: align by hand (1 KB of slack is allocated)
     unsigned char *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -268,7 +262,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) {
-            mbar_init(smem_u32(&bars->full_a[s]), TC_PRODUCERS);  // the A-producer threads
+            mbar_init(smem_u32(&bars->full_a[s]), (FLAGS & 4) ? 1 : TC_PRODUCERS);  // the A-producer threads (or the TMA issuer)
             mbar_init(smem_u32(&bars->empty_a[s]), 1);            // tcgen05.commit
         }
         for (int kb = 0; kb < TC_MAX_KB; ++kb) {
@@ -601,6 +595,32 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
                 a.prof[blockIdx.x * 8 + 5] = pq1 << 10;
                 a.prof[blockIdx.x * 8 + 6] = pq2 << 10;
             }
+        }
+    } else if (FLAGS & 4) {
+        // ================= A by TMA: 128 consecutive query rows per k-block =================
+        // (rows behind the last query and the columns behind `dim` are zero-filled by the out-of-bounds rule)
+        if (warp == TC_EPI_WARPS + 2) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t a_base = smem_u32(sA);
+            TileCursor tc;
+            tc.init(a.items, n_items, blockIdx.x, gridDim.x);
+            while (tc.valid) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_prof(smem_u32(&bars->empty_a[stage]), phase ^ 1u, prof_on, pw0);
+                    if (elect_one()) {
+                        const uint32_t fa = smem_u32(&bars->full_a[stage]);
+                        mbar_expect_tx(fa, (uint32_t)TC_A_BYTES);
+                        tma_load_2d(a_base + stage * TC_A_BYTES, &tmap_q, kb * TC_BK, tc.qb * TC_BM, fa);
+                    }
+                    __syncwarp();
+                    if (++stage == (uint32_t)n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc.advance();
+            }
+            if (prof_on && lane == 0) a.prof[blockIdx.x * 8 + 5] = pw0;
         }
     } else {
         // ================= A producers: gather 128 query rows per k-block =================
@@ -1311,11 +1331,11 @@ static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, cons
     CUtensorMap map;
     memcpy(&map, ix.tmap_storage, sizeof map);
     static const int v_epi2 = getenv("SOLO_TC_EPI2") ? 1 : 0;
-    void (*kern)(const CUtensorMap, TcScanArgs) = nullptr;
+    void (*kern)(const CUtensorMap, const CUtensorMap, TcScanArgs) = nullptr;
     if (num_kb == 13) kern = v_epi2 ? scan_tc_kernel<0, 13, 2, 3> : scan_tc_kernel<0, 13, 1, 3>;
     else kern = scan_tc_kernel<0, 0, 1, 3>;
     SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
+    kern<<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, map, a);   // (no query map: gathered groups)
     SOLO_CUDA(cudaGetLastError());
     h->launches += 3;
     tc_prof_report(h, "scan", kNumSMs);
@@ -1346,22 +1366,30 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
                  hybrid, all);
 }
 
-// K2 on the tensor cores: approximate scores of every query against every centroid,
-// out[q * ld + c] (ld = nlist rounded up to 32). The centroid table is scanned like one inverted
-// list whose query group is the whole batch.
+// K2 on the tensor cores: approximate scores of every query against the centroids [0, n_lists) (n_lists < 0: all).
+// The centroid table is scanned like one inverted list whose query group is the whole batch, so the A tiles are
+// consecutive query rows and come in by TMA. Two forms:
+//   dense (tau == null): out[q * ld + c] (ld a multiple of 32);
+//   thresholded (tau != null): only scores >= tau[q] leave the SM, appended as (score, centroid) pairs to
+//   buf[q * cap ..] with cnt[q] counting them (cnt may exceed cap: the caller checks) — no (Q, nlist) matrix.
 void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int nq, int q_scale_log2,
-                      float *out, int ld) {
+                      float *out, int ld, int n_lists, const float *tau, unsigned long long *buf, int32_t *cnt, int cap) {
     SOLO_REQUIRE(ix.tmap_cent_valid, SOLO_ESTATE, "centroid tensor map missing");
     int nb, stages;
     tc_smem_plan(ix, &nb, &stages, 64);  // every centroid chunk sees every query: short chunks, deep query ring
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     const int n_items = div_up(ix.nlist, nb);
-    if (ix.coarse_items_nq != nq) {  // descriptors are tiny: built on the host, [count pair | items], cached per nq
-        std::vector<unsigned char> hbuf(sizeof(int64_t) * 2 + (size_t)n_items * sizeof(TcItem));
+    const int n_used = n_lists < 0 ? (ix.coarse_items_used > 0 ? std::min(ix.coarse_items_used, n_items) : n_items)
+                                   : std::min(n_items, div_up(n_lists, nb));
+    constexpr int HDR = 4;  // int64 header: [0, all items, 0, items of the sampled prefix]
+    if (ix.coarse_items_nq != nq || ix.coarse_items_used != n_used) {  // descriptors are tiny: built on the host, cached
+        std::vector<unsigned char> hbuf(sizeof(int64_t) * HDR + (size_t)n_items * sizeof(TcItem));
         int64_t *hoff = reinterpret_cast<int64_t *>(hbuf.data());
         hoff[0] = 0;
         hoff[1] = n_items;
-        TcItem *hit = reinterpret_cast<TcItem *>(hbuf.data() + 2 * sizeof(int64_t));
+        hoff[2] = 0;
+        hoff[3] = n_used;
+        TcItem *hit = reinterpret_cast<TcItem *>(hbuf.data() + HDR * sizeof(int64_t));
         for (int i = 0; i < n_items; ++i) {
             hit[i].p0 = i * nb;
             hit[i].nv = std::min(nb, ix.nlist - i * nb);
@@ -1372,12 +1400,13 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
         ix.coarse_items.ensure(hbuf.size());
         SOLO_CUDA(cudaMemcpy(ix.coarse_items.p, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice));
         ix.coarse_items_nq = nq;
+        ix.coarse_items_used = n_used;
     }
     DevBuf &items = ix.coarse_items;
     TcScanArgs a;
     memset(&a, 0, sizeof a);
-    a.items = reinterpret_cast<const TcItem *>(items.as<unsigned char>() + 2 * sizeof(int64_t));
-    a.item_off = items.as<int64_t>();
+    a.items = reinterpret_cast<const TcItem *>(items.as<unsigned char>() + HDR * sizeof(int64_t));
+    a.item_off = items.as<int64_t>() + (n_lists < 0 ? 0 : 2);
     a.gq = nullptr;
     a.qh = qh;
     a.qmask = qmask;
@@ -1389,17 +1418,88 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
     a.dense_out = out;
     a.dense_ld = ld;
+    a.tau = tau;
+    a.buf = buf;
+    a.cnt = cnt;
+    a.cap = cap;
     a.prof = tc_prof_buffer();
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
+    CUtensorMap map, qmap;
+    memcpy(&map, ix.tmap_cent_storage, sizeof map);
+    static const bool v_gather = getenv("SOLO_COARSE_GATHER") != nullptr;   // cross-check: the 16-byte gather for A
+    alignas(64) unsigned char qstore[128];
+    if (!v_gather) tc_encode_rows(qstore, qh, ix.dim, nq, TC_BM);
+    memcpy(&qmap, v_gather ? (const void *)ix.tmap_cent_storage : (const void *)qstore, sizeof qmap);
+    void (*kern)(const CUtensorMap, const CUtensorMap, TcScanArgs);
+    if (tau) {
+        if (v_gather) kern = num_kb == 13 ? scan_tc_kernel<0, 13, 1, 3> : scan_tc_kernel<0, 0, 1, 3>;
+        else kern = num_kb == 13 ? scan_tc_kernel<0, 13, 1, 7> : scan_tc_kernel<0, 0, 1, 7>;
+    } else {
+        if (v_gather) kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 3> : scan_tc_kernel<1, 0, 1, 3>;
+        else kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 7> : scan_tc_kernel<1, 0, 1, 7>;
+    }
+    SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<std::min(kNumSMs, n_lists < 0 ? n_items : n_used), TC_THREADS, smem, h->stream>>>(map, qmap, a);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 1;
+    tc_prof_report(h, "coarse", std::min(kNumSMs, n_items));
+}
+
+// Fall-back of the compact probe selection: dense coarse scores for the queries of a device-side list (n_fail of
+// them, known only on the device: the items are rewritten there, no host round trip). Rows land at out[q * ld].
+__global__ void coarse_fallback_items_kernel(const TcItem *__restrict__ src, int n_items, const int32_t *__restrict__ n_fail,
+                                             TcItem *__restrict__ dst, int64_t *__restrict__ hdr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nf = *n_fail;
+    if (i == 0) {
+        hdr[0] = 0;
+        hdr[1] = nf > 0 ? n_items : 0;
+    }
+    if (i < n_items) {
+        TcItem it = src[i];
+        it.G = nf;
+        dst[i] = it;
+    }
+}
+
+void launch_coarse_tc_listed(solo_handle *h, IvfIndex &ix, const __half *qh, const uint32_t *qmask, int q_scale_log2,
+                             float *out, int ld, const int32_t *q_list, const int32_t *n_listed) {
+    SOLO_REQUIRE(ix.tmap_cent_valid && ix.coarse_items_nq >= 0, SOLO_ESTATE, "coarse items missing");
+    int nb, stages;
+    tc_smem_plan(ix, &nb, &stages, 64);
+    const int n_items = div_up(ix.nlist, nb);
+    constexpr int HDR = 4;
+    DevBuf &fb = ix.coarse_fb_items;
+    fb.ensure(2 * sizeof(int64_t) + (size_t)n_items * sizeof(TcItem));
+    TcItem *fb_items = reinterpret_cast<TcItem *>(fb.as<unsigned char>() + 2 * sizeof(int64_t));
+    coarse_fallback_items_kernel<<<div_up(n_items, 256), 256, 0, h->stream>>>(
+        reinterpret_cast<const TcItem *>(ix.coarse_items.as<unsigned char>() + HDR * sizeof(int64_t)), n_items, n_listed,
+        fb_items, fb.as<int64_t>());
+    TcScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.items = fb_items;
+    a.item_off = fb.as<int64_t>();
+    a.gq = q_list;
+    a.qh = qh;
+    a.qmask = qmask;
+    a.nlist = 1;
+    a.dim = ix.dim;
+    a.nb = nb;
+    a.stages = stages;
+    a.kbb = 2;
+    a.inv_scale = ldexpf(1.f, -(ix.cent_scale_log2 + q_scale_log2));
+    a.dense_out = out;
+    a.dense_ld = ld;
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
     const size_t smem = (size_t)stages * TC_A_BYTES + (size_t)num_kb * nb * 128 + sizeof(TcBarriers) + 1024;
     CUtensorMap map;
     memcpy(&map, ix.tmap_cent_storage, sizeof map);
     auto kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 3> : scan_tc_kernel<1, 0, 1, 3>;
     SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<std::min(kNumSMs, n_items), TC_THREADS, smem, h->stream>>>(map, a);
+    kern<<<std::min(kNumSMs, n_items), TC_THREADS, smem, h->stream>>>(map, map, a);
     SOLO_CUDA(cudaGetLastError());
-    h->launches += 1;
-    tc_prof_report(h, "coarse", std::min(kNumSMs, n_items));
+    h->launches += 2;
 }
 
 }  // namespace solo

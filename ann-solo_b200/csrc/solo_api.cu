@@ -350,6 +350,8 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_pairs = value != 0;
         } else if (strcmp(key, "front_probes") == 0) {
             h->opt_front_probes = value != 0;
+        } else if (strcmp(key, "compact_probes") == 0) {
+            h->opt_compact_probes = value != 0;
         } else if (strcmp(key, "tc_nb") == 0) {
             SOLO_REQUIRE(value >= 0 && value <= 256 && value % 32 == 0, SOLO_EINVAL, "tc_nb must be a multiple of 32 in [0, 256]");
             h->opt_tc_nb = (int)value;

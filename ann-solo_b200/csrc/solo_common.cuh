@@ -171,6 +171,8 @@ struct IvfIndex {
     int cent_scale_log2 = 10;  // cent_h holds centroid * 2^cent_scale_log2
     DevBuf coarse_items;       // work items of the tensor-core coarse pass, valid for coarse_items_nq queries
     int coarse_items_nq = -1;
+    int coarse_items_used = -1;
+    DevBuf coarse_fb_items;    // the same items with a device-written group size (fall-back of the compact probe selection)
 };
 
 }  // namespace solo
@@ -189,6 +191,8 @@ struct solo_handle {
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
     int opt_round0_scores = 4096;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
+    bool opt_compact_probes = true; // thresholded coarse pass + compact probe selection (no (Q, nlist) score matrix)
+    int64_t compact_probe_batches = 0;
     int opt_tc_nb = 0;              // > 0: rows of the resident list chunk of the tcgen05 scan (multiple of 32; tuning)
     int opt_tc_kbb = 2;             // k-blocks per MMA issue batch of the tcgen05 scan (tuning)
     solo::StageProf prof[solo::ST_COUNT];

@@ -121,3 +121,34 @@ def test_faiss_like_index_api(engine, oracle, synth):
     assert I.dtype == np.int64 and D.dtype == np.float32 and (I[:, 0] == np.arange(10)).all()
     index.reset()
     assert index.ntotal == 0
+
+
+def test_compact_probe_selection_equals_dense(engine, oracle, synth):
+    """K2's compact path (sampled per-query threshold, thresholded coarse pass, selection over the surviving pairs)
+    against the dense (Q, nlist) path and the oracle: identical top-k ids and score bits. Zero and duplicated query
+    vectors force the device-side fall-back (threshold 0 -> every list passes -> dense rows for that query)."""
+    slot, nlist, nprobe, k = CH + 7, 2048, 128, 64
+    lib = synth.make_library(30000, decoy_fraction=0.25, seed=91, decoy_seed=92)
+    x = oracle.vectorize(lib["mz"], lib["inten"], lib["off"])
+    cent = oracle.kmeans(x, nlist, seed=4, iters=2)
+    engine.ivf_set_centroids(slot, cent)
+    engine.ivf_add(slot, x)
+    assign = oracle.ivf_assign(x, cent)
+    off, ids, vecs = oracle.build_lists(x, assign, nlist)
+    q = synth.make_queries(lib, 400, seed=93)
+    qv = oracle.vectorize(q["mz"], q["inten"], q["off"])
+    qv[5] = 0.0                      # all coarse scores 0: the sampled threshold passes every list
+    qv[6] = cent[17]                 # a centroid itself
+    qv[7, :] = 0.0
+    qv[7, 3] = 1.0                   # one non-zero dimension: most scores are exactly 0 (ties at the threshold)
+    try:
+        engine.set_option("compact_probes", 1)
+        D1, I1 = engine.ivf_search(slot, qv, k, nprobe)
+        engine.set_option("compact_probes", 0)
+        D0, I0 = engine.ivf_search(slot, qv, k, nprobe)
+    finally:
+        engine.set_option("compact_probes", 1)
+    assert np.array_equal(I1, I0) and np.array_equal(D1.view(np.uint32), D0.view(np.uint32))
+    Dw, Iw = oracle.ivf_search(qv, cent, off, ids, vecs, nprobe, k)
+    assert np.array_equal(I1, Iw) and np.array_equal(D1.view(np.uint32), Dw.view(np.uint32))
+    engine.ivf_reset(slot)
