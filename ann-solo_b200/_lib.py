@@ -87,6 +87,7 @@ SYMBOLS = {
     "solo_fetch_results_range": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "solo_search_batch": (C.c_int, [_vp, C.c_int, C.POINTER(SearchParams), _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "solo_reserve_slot": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int]),
     "solo_stage_queries_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "solo_fetch_results_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "solo_wait_results": (C.c_int, [_vp, C.c_int]),

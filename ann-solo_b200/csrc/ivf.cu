@@ -1239,6 +1239,7 @@ void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nl
     h->launches++;
     ivf_reset(ix);
     ix.coarse_items_nq = -1;
+    ix.coarse_items_used = -1;
     SOLO_CUDA(cudaStreamSynchronize(h->stream));
     tc_make_centroid_map(ix);
 }

@@ -301,7 +301,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
         float thr = INFINITY;
         if (tc.valid) {
             const int gi = tc.qb * TC_BM + row;
-            q = gi < tc.cur.G ? (a.gq ? a.gq[tc.cur.g0 + gi] : gi) : -1;
+            q = gi < tc.cur.G ? (a.gq ? a.gq[tc.cur.g0 + gi] : tc.cur.g0 + gi) : -1;
             if (MODE == 0 && q >= 0) thr = a.tau[q] * scale;
         }
         while (tc.valid) {
@@ -312,7 +312,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
             int q_next = -1;
             if (nx.valid) {
                 const int gi = nx.qb * TC_BM + row;
-                q_next = gi < nx.cur.G ? (a.gq ? a.gq[nx.cur.g0 + gi] : gi) : -1;
+                q_next = gi < nx.cur.G ? (a.gq ? a.gq[nx.cur.g0 + gi] : nx.cur.g0 + gi) : -1;
             }
             const int buf = set;
             mbar_wait_prof(smem_u32(&bars->tmem_full[buf]), (unit >> 1) & 1, prof_on, pw0);
@@ -610,7 +610,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                     if (elect_one()) {
                         const uint32_t fa = smem_u32(&bars->full_a[stage]);
                         mbar_expect_tx(fa, (uint32_t)TC_A_BYTES);
-                        tma_load_2d(a_base + stage * TC_A_BYTES, &tmap_q, kb * TC_BK, tc.qb * TC_BM, fa);
+                        tma_load_2d(a_base + stage * TC_A_BYTES, &tmap_q, kb * TC_BK, tc.cur.g0 + tc.qb * TC_BM, fa);
                     }
                     __syncwarp();
                     if (++stage == (uint32_t)n_stages) {
@@ -647,7 +647,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
             for (int i = 0; i < NR; ++i) {
                 const int gi = rbase + RSTEP * i;
                 const bool real = gi < tc.cur.G;
-                const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : tc.cur.g0 + (real ? gi : 0);
                 src[i] = qh_c + (size_t)q * row_bytes;
                 nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;  // padding rows are zero-filled
             }
@@ -664,7 +664,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                 for (int i = 0; i < NR; ++i) {
                     const int gi = tc.qb * TC_BM + rbase + RSTEP * i;
                     const bool real = gi < tc.cur.G;
-                    const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                    const int q = a.gq ? a.gq[tc.cur.g0 + (real ? gi : 0)] : tc.cur.g0 + (real ? gi : 0);
                     src[i] = qh_c + (size_t)q * row_bytes;
                     nz[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;
                 }
@@ -675,7 +675,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                     for (int i = 0; i < NR; ++i) {
                         const int gi = nx.qb * TC_BM + rbase + RSTEP * i;
                         const bool real = gi < nx.cur.G;
-                        const int q = a.gq ? a.gq[nx.cur.g0 + (real ? gi : 0)] : (real ? gi : 0);
+                        const int q = a.gq ? a.gq[nx.cur.g0 + (real ? gi : 0)] : nx.cur.g0 + (real ? gi : 0);
                         qn[i] = real ? q : -1 - q;  // negative: padding row (zero-filled)
                     }
                 }
@@ -1379,11 +1379,14 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     tc_smem_plan(ix, &nb, &stages, 64);  // every centroid chunk sees every query: short chunks, deep query ring
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
     const int n_items = div_up(ix.nlist, nb);
-    const int n_used = n_lists < 0 ? (ix.coarse_items_used > 0 ? std::min(ix.coarse_items_used, n_items) : n_items)
-                                   : std::min(n_items, div_up(n_lists, nb));
-    constexpr int HDR = 4;  // int64 header: [0, all items, 0, items of the sampled prefix]
-    if (ix.coarse_items_nq != nq || ix.coarse_items_used != n_used) {  // descriptors are tiny: built on the host, cached
-        std::vector<unsigned char> hbuf(sizeof(int64_t) * HDR + (size_t)n_items * sizeof(TcItem));
+    // the sampled prefix is only a few chunks: its items also split the query range (512 queries each) so that
+    // the pass still fills the machine; they are stored behind the full-table items
+    const int n_pref_chunks = n_lists < 0 ? std::max(ix.coarse_items_used, 0) : std::min(n_items, div_up(n_lists, nb));
+    const int q_span = 4 * TC_BM, n_spans = div_up(nq, q_span);
+    const int n_used = n_pref_chunks * n_spans;
+    constexpr int HDR = 4;  // int64 header: [0, items of the full table | 0, items of the sampled prefix]
+    if (ix.coarse_items_nq != nq || (n_lists >= 0 && ix.coarse_items_used != n_pref_chunks)) {  // tiny: built on the host, cached
+        std::vector<unsigned char> hbuf(sizeof(int64_t) * HDR + (size_t)(n_items + n_used) * sizeof(TcItem));
         int64_t *hoff = reinterpret_cast<int64_t *>(hbuf.data());
         hoff[0] = 0;
         hoff[1] = n_items;
@@ -1396,16 +1399,24 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
             hit[i].g0 = 0;
             hit[i].G = nq;
         }
+        for (int c = 0; c < n_pref_chunks; ++c)
+            for (int sp = 0; sp < n_spans; ++sp) {
+                TcItem &t = hit[n_items + c * n_spans + sp];
+                t.p0 = c * nb;
+                t.nv = std::min(nb, ix.nlist - c * nb);
+                t.g0 = sp * q_span;
+                t.G = std::min(q_span, nq - sp * q_span);
+            }
         SOLO_CUDA(cudaStreamSynchronize(h->stream));  // earlier launches may still read the old descriptors
         ix.coarse_items.ensure(hbuf.size());
         SOLO_CUDA(cudaMemcpy(ix.coarse_items.p, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice));
         ix.coarse_items_nq = nq;
-        ix.coarse_items_used = n_used;
+        ix.coarse_items_used = n_pref_chunks;
     }
     DevBuf &items = ix.coarse_items;
     TcScanArgs a;
     memset(&a, 0, sizeof a);
-    a.items = reinterpret_cast<const TcItem *>(items.as<unsigned char>() + HDR * sizeof(int64_t));
+    a.items = reinterpret_cast<const TcItem *>(items.as<unsigned char>() + HDR * sizeof(int64_t)) + (n_lists < 0 ? 0 : n_items);
     a.item_off = items.as<int64_t>() + (n_lists < 0 ? 0 : 2);
     a.gq = nullptr;
     a.qh = qh;
@@ -1433,14 +1444,16 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     memcpy(&qmap, v_gather ? (const void *)ix.tmap_cent_storage : (const void *)qstore, sizeof qmap);
     void (*kern)(const CUtensorMap, const CUtensorMap, TcScanArgs);
     if (tau) {
-        if (v_gather) kern = num_kb == 13 ? scan_tc_kernel<0, 13, 1, 3> : scan_tc_kernel<0, 0, 1, 3>;
-        else kern = num_kb == 13 ? scan_tc_kernel<0, 13, 1, 7> : scan_tc_kernel<0, 0, 1, 7>;
+        // (two 32-column groups per reservation: one atomic per query row and 64-centroid chunk)
+        if (v_gather) kern = num_kb == 13 ? scan_tc_kernel<0, 13, 2, 3> : scan_tc_kernel<0, 0, 2, 3>;
+        else kern = num_kb == 13 ? scan_tc_kernel<0, 13, 2, 7> : scan_tc_kernel<0, 0, 2, 7>;
     } else {
         if (v_gather) kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 3> : scan_tc_kernel<1, 0, 1, 3>;
         else kern = num_kb == 13 ? scan_tc_kernel<1, 13, 1, 7> : scan_tc_kernel<1, 0, 1, 7>;
     }
     SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<std::min(kNumSMs, n_lists < 0 ? n_items : n_used), TC_THREADS, smem, h->stream>>>(map, qmap, a);
+    (void)n_pref_chunks;
     SOLO_CUDA(cudaGetLastError());
     h->launches += 1;
     tc_prof_report(h, "coarse", std::min(kNumSMs, n_items));

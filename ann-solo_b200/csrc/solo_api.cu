@@ -1031,6 +1031,25 @@ int solo_search_batch(solo_handle *h, int charge, const solo_search_params *p, c
 }
 
 // ---- streaming: copies of batch i+1 / i-1 under the kernels of batch i ------------------------------------------
+int solo_reserve_slot(solo_handle *h, int nq, int64_t n_peaks, int max_pairs, int mz_is_f64) {
+    if (!h) return SOLO_EINVAL;
+    return guarded(h, [&] {
+        SOLO_REQUIRE(nq >= 0 && n_peaks >= 0 && max_pairs >= 0, SOLO_EINVAL, "negative size");
+        // growing a buffer frees and allocates (a device-wide synchronisation): done here, ahead of the stream
+        h->q_mz.ensure(std::max<size_t>(n_peaks * 4, 16));
+        h->q_int.ensure(std::max<size_t>(n_peaks * 4, 16));
+        h->q_off.ensure((size_t)(nq + 1) * 8);
+        h->q_prec_mz.ensure(std::max<size_t>((size_t)nq * 8, 16));
+        if (mz_is_f64) h->q_mz_vec.ensure(std::max<size_t>(n_peaks * 8, 16));
+        h->r_best_row.ensure(std::max(nq, 1) * sizeof(int32_t));
+        h->r_best_score.ensure(std::max(nq, 1) * sizeof(double));
+        h->r_n_pairs.ensure(std::max(nq, 1) * sizeof(int32_t));
+        h->r_n_cand.ensure(std::max(nq, 1) * sizeof(int32_t));
+        h->r_pairs.ensure((size_t)std::max(nq, 1) * std::max(max_pairs, 1) * 2 * sizeof(uint32_t));
+        h->r_ovf.ensure(16);
+    });
+}
+
 int solo_stage_queries_async(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
                              const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64) {
     if (!h) return SOLO_EINVAL;

@@ -332,27 +332,58 @@ class SoloEngine:
         dict of result arrays to fill (page-locked buffers make the copies asynchronous). The host->device copy of
         batch i+1 and the device->host copy of batch i-1 run on the copy stream under the kernels of batch i.
         Yields ``(charge, results)`` in input order; the result arrays of a batch are complete when it is yielded."""
+        import os
+        import time
+        trace = [] if os.environ.get("SOLO_STREAM_TRACE") == "1" else None
         it = iter(batches)
         prev_slot = self._slot if hasattr(self, "_slot") else 0
         nxt = next(it, None)
+        # both slots are kept as large as the largest batch seen so far (a buffer that has to grow in mid-stream
+        # costs a device-wide synchronisation)
+        cap = getattr(self, "_stream_cap", [0, 0, 0, 0])
+
+        def reserve(q):
+            want = [len(q["off"]) - 1, int(q["off"][-1]), params.max_pairs, int(q.get("mz_vec") is not None)]
+            if any(w > c for w, c in zip(want, cap)):
+                cap[:] = [max(w, c) for w, c in zip(want, cap)]
+                keep = self._slot if hasattr(self, "_slot") else 0
+                for s_ in slots:
+                    self.select_slot(s_)
+                    self._check(self._lib.solo_reserve_slot(self._h, cap[0], cap[1], cap[2], cap[3]))
+                self.select_slot(keep)
+            self._stream_cap = cap
+
         if nxt is not None:
+            reserve(nxt[1])
             self.select_slot(slots[0])
             self.stage_queries_async(nxt[1], nxt[1].get("mz_vec"))
         i = 0
         pending = None   # (slot, charge, out) of the batch whose fetch is in flight
         while nxt is not None:
             cur, nxt = nxt, next(it, None)
+            t0 = time.perf_counter()
             if nxt is not None:
+                reserve(nxt[1])
                 self.select_slot(slots[(i + 1) % 2])
                 self.stage_queries_async(nxt[1], nxt[1].get("mz_vec"))
+            t1 = time.perf_counter()
             self.select_slot(slots[i % 2])
             self.search_staged(cur[0], params)
+            t2 = time.perf_counter()
             out = self.fetch_results_async(cur[2] if len(cur) > 2 else None)
+            t3 = time.perf_counter()
             if pending is not None:
                 self.wait_results(pending[0])
+                if trace is not None:
+                    trace.append((cur[0], t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
                 yield pending[1], pending[2]
             pending = (slots[i % 2], cur[0], out)
             i += 1
+        if trace:
+            import sys
+            print("[search_stream] host ms per batch (charge: stage_async / search_staged / fetch_async / wait_results): " +
+                  "  ".join(f"{z}: {a * 1e3:.2f}/{b * 1e3:.2f}/{c * 1e3:.2f}/{d * 1e3:.2f}" for z, a, b, c, d in trace[:12]),
+                  file=sys.stderr)
         if pending is not None:
             self.wait_results(pending[0])
             yield pending[1], pending[2]

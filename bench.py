@@ -212,7 +212,7 @@ def run_solo(args, wl, rank, world, local_rank):
 
     def timed(step_fn, steps, warmup, profile=False, streamed=False):
         for _ in range(warmup):
-            step_fn()
+            step_fn(2) if streamed else step_fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ncu = profile and os.environ.get("SOLO_NCU") == "1"  # ncu --profile-from-start off
@@ -282,8 +282,17 @@ def run_solo(args, wl, rank, world, local_rank):
                 pc = np.percentile(cnt, [1, 50, 90, 99, 100]).astype(int).tolist()
                 log(f"   z={z}: scan-buffer entries/query p1/p50/p90/p99/max = {pc} mean={cnt.mean():.0f}")
     ms_res, prof, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
-    ms_e2e, prof_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), profile=True, streamed=True)
-    log("e2e stages (ms/step): " + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof_e2e.items() if v["ms"] > 0))
+    e2e_prof = os.environ.get("SOLO_BENCH_E2E_PROFILE") == "1"   # diagnostic: stage times of the streamed leg
+    ms_e2e, prof_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), profile=e2e_prof, streamed=True)
+    if e2e_prof:
+        log("e2e stages (ms/step): " + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof_e2e.items() if v["ms"] > 0))
+    if os.environ.get("SOLO_BENCH_E2E_SYNC") == "1":             # diagnostic: the synchronous one-call API instead
+        def step_sync():
+            for z in charges:
+                eng.select_slot(z)
+                eng.search_batch(z, params, host_q[z], out=host_out[z])
+        ms_sync, _, _, _ = timed(step_sync, args.steps, 1)
+        log(f"e2e through the synchronous solo_search_batch: {ms_sync / args.steps:.3f} ms/step (streamed: {ms_e2e / args.steps:.3f})")
     log("resident stages (ms/step): " + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof.items() if v["ms"] > 0))
     value = world * nq_rank * args.steps / (ms_res / 1e3)
     e2e = world * nq_rank * args.steps / (ms_e2e / 1e3)

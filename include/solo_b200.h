@@ -299,6 +299,9 @@ int solo_ssm_features_staged(solo_handle *h, int charge, const int32_t *q_prec_c
  * stay untouched until solo_wait_results(slot) returns. Typical loop with two slots:
  *   select(s[(i+1)%2]); stage_async(batch i+1);  select(s[i%2]); search_staged(batch i); fetch_async(out i);
  *   wait_results(s[(i-1)%2]);  -> results of batch i-1 are on the host */
+/* Grows the active slot's device buffers for batches of up to nq queries / n_peaks peaks (growing later would
+ * free and allocate inside the stream, a device-wide synchronisation). */
+int solo_reserve_slot(solo_handle *h, int nq, int64_t n_peaks, int max_pairs, int mz_is_f64);
 int solo_stage_queries_async(solo_handle *h, const float *q_mz, const void *q_mz_vec, const float *q_intensity,
                              const int64_t *q_off, const double *q_prec_mz, int nq, int mz_is_f64);
 int solo_fetch_results_async(solo_handle *h, int32_t *best_row, double *best_score, int32_t *n_pairs, uint32_t *pairs,
