@@ -959,7 +959,9 @@ __device__ __forceinline__ bool window_pass(const FinalArgs &a, int q, int id) {
 // With an exact scan engine (eps.rel == 0) step 2 is the identity.
 constexpr int TK_BCAP = 1024;  // band entries re-scored on chip by the fast path of final_topk_kernel
 
-__global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
+// (two 1024-thread CTAs per SM: 32 registers per thread, so that three 512-thread CTAs of the common launch stay resident)
+template <bool PACKED>
+__global__ void __launch_bounds__(TK_THREADS, 2) final_topk_kernel(FinalArgs a) {
     extern __shared__ uint32_t s_keys[];  // [scap] decision keys; s_q [d] follows; then s_sorted [IVF_MAX_K] (sorted output)
     __shared__ uint32_t s_hist[KTH_BINS];
     __shared__ uint32_t s_bc[KTH_BC];
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     // list position -> library row (the merge of mode B runs on row ids directly: list_ids == null)
     auto row_of = [&](uint32_t pos) -> int { return a.list_ids ? a.list_ids[pos] : (int)pos; };
     auto emit = [&](int id, float score) {
-        if (a.packed)
+        if (PACKED)
             a.packed[(int64_t)q * a.k + atomicAdd(&s_nout, 1)] =
                 ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(uint32_t)id;
         else if (window_pass(a, q, id))
@@ -1048,7 +1050,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
                 if (r < need) emit((int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)), ivf_o2f((uint32_t)(key >> 32)));
             }
             __syncthreads();
-            if (a.packed) {
+            if (PACKED) {
                 for (int i = s_nout + threadIdx.x; i < a.k; i += blockDim.x) a.packed[(int64_t)q * a.k + i] = IVF_PACKED_PAD;
             } else if (threadIdx.x == 0) {
                 a.sel_cnt[q] = s_nout;
@@ -1093,7 +1095,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
                     int slot = atomicAdd(&s_nout, 1);
                     s_sorted[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
                 } else {   // a "certainly in" key carries no score: the entry's own (approximate) one is reported
-                    emit(id, key == 0xFFFFFFFFu ? __uint_as_float((uint32_t)(e >> 32)) : ivf_o2f(key));
+                    emit(id, PACKED ? (key == 0xFFFFFFFFu ? __uint_as_float((uint32_t)(e >> 32)) : ivf_o2f(key)) : 0.f);
                 }
             }
         }
@@ -1126,7 +1128,7 @@ __global__ void __launch_bounds__(TK_THREADS) final_topk_kernel(FinalArgs a) {
     }
     __syncthreads();
     if (!sorted_out) {
-        if (a.packed) {
+        if (PACKED) {
             for (int i = s_nout + threadIdx.x; i < a.k; i += blockDim.x) a.packed[(int64_t)q * a.k + i] = IVF_PACKED_PAD;
         } else if (threadIdx.x == 0) {
             a.sel_cnt[q] = s_nout;
@@ -1656,7 +1658,8 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
     const int scap_fin = std::min(cap, std::max(1024, env_scap));
     const size_t tk_smem = tk_bytes(cap);
     SOLO_CUDA(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
-    SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
+    auto final_kern = a.packed ? final_topk_kernel<true> : final_topk_kernel<false>;
+    SOLO_CUDA(cudaFuncSetAttribute(final_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem));
     // expected scanned vectors per query, for the flop figure of the stage
     const double scan_units = 2.0 * d * (double)nq * ((double)ix.nstored * nprobe / nlist);
 
@@ -1713,7 +1716,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
             StageTimer t(h, ST_TOPK, 1);
             fa.scap = scap_fin;
             fa.min_cnt = -1;
-            final_topk_kernel<<<nq, 512, tk_bytes(scap_fin), st>>>(fa);
+            final_kern<<<nq, 512, tk_bytes(scap_fin), st>>>(fa);
             SOLO_CUDA(cudaGetLastError());
         }
         // A query whose candidate buffer overflowed was not finished: raise its threshold from
@@ -1727,7 +1730,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
             StageTimer t(h, ST_TOPK, 1);
             fa.scap = cap;
             fa.min_cnt = scap_fin;
-            final_topk_kernel<<<nq, TK_THREADS, tk_smem, st>>>(fa);
+            final_kern<<<nq, TK_THREADS, tk_smem, st>>>(fa);
             SOLO_CUDA(cudaGetLastError());
             SOLO_CUDA(cudaMemcpyAsync(n_flags, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             SOLO_CUDA(cudaStreamSynchronize(st));
@@ -1809,8 +1812,8 @@ void ivf_merge_select(solo_handle *h, IvfIndex &ix, const unsigned long long *d_
     fa.sp_idx = ix.row_idx.as<uint16_t>();
     fa.sp_val = ix.row_val.as<float>();
     const size_t smem = (size_t)cap * sizeof(uint32_t) + (size_t)((ix.dim + 1) & ~1) * sizeof(float);
-    SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_topk_kernel<<<n, cap <= 16384 ? 512 : TK_THREADS, smem, h->stream>>>(fa);
+    SOLO_CUDA(cudaFuncSetAttribute(final_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_topk_kernel<false><<<n, cap <= 16384 ? 512 : TK_THREADS, smem, h->stream>>>(fa);
     SOLO_CUDA(cudaGetLastError());
 }
 

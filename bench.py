@@ -321,10 +321,11 @@ def run_solo(args, wl, rank, world, local_rank):
     flops_per_launch = scan["units"] / max(scan["launches"], 1)
     achieved = flops_per_launch / (scan_ms_per_launch * 1e-3) / 1e12 if scan_ms_per_launch > 0 else 0.0
     # DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(
-            "k3_list_scan_dram_bytes_per_launch")
+    traffic, tr_all = None, {}
+    try:   # written by profiles/export_ncu.py from the committed `ncu --set full` capture (carries the build's git hash)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        traffic = tr.get("k3_list_scan_dram_bytes_per_launch")
+        tr_all = tr.get("per_kernel_dram_bytes_per_launch", {})
     except (OSError, ValueError):
         pass
     roofline = {"kernel": "k3_list_scan", "bound": "tensor", "achieved": round(achieved, 3), "peak": peak_tf,
@@ -332,6 +333,25 @@ def run_solo(args, wl, rank, world, local_rank):
                 "ms_per_launch": round(scan_ms_per_launch, 4), "launches": scan["launches"],
                 "share_of_step": round(scan["ms"] / ms_res, 4)}
     stages = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
+    # the other two kernels with a roofline of their own: K2 coarse scoring (tensor: 2 d nlist flops per
+    # query) and K5 (HBM gather: 9 P_c + 24 bytes per scored (query, candidate) pair, P_c = peaks of the candidate)
+    hbm_gbs = peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6500.0))
+    coarse = prof["coarse"]
+    coarse_tf = coarse["units"] / (coarse["ms"] * 1e-3) / 1e12 if coarse["ms"] > 0 else 0.0
+    pairs_scored = float(sum(int(host_out[z]["n_cand"].sum()) for z in charges))
+    mean_pc = float(np.mean([np.diff(per_charge[z][0]["off"]).mean() for z in charges]))
+    k5_bytes = pairs_scored * (9.0 * mean_pc + 24.0)
+    k5_ms = prof["score"]["ms"] / args.steps
+    k5_gbs = k5_bytes / (k5_ms * 1e-3) / 1e9 if k5_ms > 0 else 0.0
+    roofline_all = [
+        dict(roofline),
+        {"kernel": "k2_coarse (thresholded tcgen05 pass incl. the sampled prefix)", "bound": "tensor", "achieved": round(coarse_tf, 3),
+         "peak": peak_tf, "unit": "TFLOP/s", "frac": round(coarse_tf / peak_tf, 5), "ms_per_step": round(coarse["ms"] / args.steps, 4),
+         "traffic": tr_all.get("k2_coarse")},
+        {"kernel": "k5_fast_kernel (shifted dot)", "bound": "hbm", "achieved": round(k5_gbs, 1), "peak": hbm_gbs, "unit": "GB/s",
+         "frac": round(k5_gbs / hbm_gbs, 5), "ms_per_step": round(k5_ms, 4), "pairs_per_step": int(pairs_scored),
+         "algorithmic_bytes_per_pair": round(9.0 * mean_pc + 24.0, 1), "traffic": tr_all.get("k5_fast_kernel")},
+    ]
 
     # the CPU baseline is reported by the single-GPU run only (torchrun also pins OMP_NUM_THREADS=1)
     cpu, parity = (cpu_baseline(wl, per_charge, q_by_charge, eng, host_out)
@@ -347,8 +367,8 @@ def run_solo(args, wl, rank, world, local_rank):
                    "l2": "index and peak store (>1 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e, 1), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stages,
-        "cpu_baseline": cpu, "parity": parity,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_all": roofline_all,
+        "stage_ms_per_step": stages, "cpu_baseline": cpu, "parity": parity,
     }
     if extras:
         line["extras"] = extras
