@@ -1866,6 +1866,20 @@ __global__ void densify_rows_kernel(const int32_t *__restrict__ rows, int nsel, 
 // the device once (`fill(r0, m, dst)` puts rows [r0, r0+m) into the dense device chunk `dst`) and
 // kept as sparse rows; every Lloyd iteration is one exact coarse-assignment pass plus one
 // deterministic centroid update. Leaves only centroids behind, like Faiss.
+// cent[dst] = cent[src] with every dimension scaled by 1 +- 1/1024 (signs from a hash of (copy, dimension)): the
+// two lists share the source's vectors at the next assignment (Faiss' split_clusters uses the same perturbation)
+__global__ void reseed_centroids_kernel(const int32_t *__restrict__ pairs, float *__restrict__ cent, int dim) {
+    const int src = pairs[3 * blockIdx.x], dst = pairs[3 * blockIdx.x + 1], copy = pairs[3 * blockIdx.x + 2];
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        uint32_t hsh = (uint32_t)(copy * 0x9E3779B1u) ^ (uint32_t)(j * 0x85EBCA77u);
+        hsh ^= hsh >> 15;
+        hsh *= 0x2C1B3C6Du;
+        hsh ^= hsh >> 12;
+        const float f = (hsh & 1u) ? 1.f + 1.f / 1024.f : 1.f - 1.f / 1024.f;
+        cent[(int64_t)dst * dim + j] = __fmul_rn(cent[(int64_t)src * dim + j], f);
+    }
+}
+
 void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist, int iters, uint64_t seed,
                     const std::function<void(int64_t, int64_t, float *)> &fill) {
     SOLO_REQUIRE(n >= nlist, SOLO_EINVAL, "need at least nlist (%d) training rows, got %lld", nlist, (long long)n);
@@ -1908,7 +1922,7 @@ void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist,
                                                       ix.cent.as<float>());
     SOLO_CUDA(cudaGetLastError());
     h->launches++;
-    for (int it = 0; it < iters; ++it) {
+    auto lloyd_iteration = [&]() {
         DevBuf &best = h->scratch[2];
         best.ensure(n * sizeof(unsigned long long));
         SOLO_CUDA(cudaMemsetAsync(best.p, 0, n * sizeof(unsigned long long), h->stream));
@@ -1924,6 +1938,36 @@ void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist,
             ix.row_val.as<float>(), dim, ix.cent.as<float>());
         SOLO_CUDA(cudaGetLastError());
         h->launches += 3;
+    };
+    for (int it = 0; it < iters; ++it) lloyd_iteration();
+    // ---- optional balancing rounds (solo_set_option("train_balance", R)): Lloyd on sparse high-dimensional data
+    // leaves a heavy tail (C2: median 33, mean 92, max 1,251 vectors per list), which costs the list scan tiles
+    // that are mostly empty. Like Faiss' split of empty clusters, the centroid of a list far below the mean is
+    // re-seeded with a slightly perturbed copy of the centroid of a list far above it (several copies for very
+    // long lists); one Lloyd iteration follows each round. Centroids are an input to parity, not a result.
+    for (int round = 0; round < h->opt_train_balance && iters > 0; ++round) {
+        std::vector<std::pair<int64_t, int>> sz(nlist);
+        for (int l = 0; l < nlist; ++l) sz[l] = {ix.h_list_off[l + 1] - ix.h_list_off[l], l};
+        std::sort(sz.begin(), sz.end());
+        const double mean = (double)ix.nstored / nlist;
+        std::vector<int32_t> pairs;  // (source list, re-seeded list, copy number)
+        int lo_i = 0;
+        for (int hi_i = nlist - 1; hi_i > lo_i && (double)sz[hi_i].first > 1.75 * mean; --hi_i) {
+            const int copies = (int)std::min<double>(15.0, std::floor((double)sz[hi_i].first / (1.25 * mean))) - 1;
+            for (int c = 0; c < std::max(copies, 1) && lo_i < hi_i && (double)sz[lo_i].first < mean / 3.0; ++c, ++lo_i) {
+                pairs.push_back(sz[hi_i].second);
+                pairs.push_back(sz[lo_i].second);
+                pairs.push_back(c + 1);
+            }
+        }
+        if (pairs.empty()) break;
+        DevBuf &dp = h->scratch[0];
+        dp.ensure(pairs.size() * sizeof(int32_t));
+        SOLO_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        reseed_centroids_kernel<<<(int)(pairs.size() / 3), 256, 0, h->stream>>>(dp.as<int32_t>(), ix.cent.as<float>(), dim);
+        SOLO_CUDA(cudaGetLastError());
+        lloyd_iteration();
+        h->launches += 1;
     }
     std::vector<float> out((size_t)nlist * dim);
     SOLO_CUDA(cudaMemcpyAsync(out.data(), ix.cent.p, out.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

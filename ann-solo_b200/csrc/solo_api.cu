@@ -350,6 +350,9 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_pairs = value != 0;
         } else if (strcmp(key, "front_probes") == 0) {
             h->opt_front_probes = value != 0;
+        } else if (strcmp(key, "train_balance") == 0) {
+            SOLO_REQUIRE(value >= 0 && value <= 64, SOLO_EINVAL, "train_balance must be in [0, 64]");
+            h->opt_train_balance = (int)value;
         } else if (strcmp(key, "compact_probes") == 0) {
             h->opt_compact_probes = value != 0;
         } else if (strcmp(key, "tc_nb") == 0) {

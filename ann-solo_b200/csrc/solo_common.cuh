@@ -191,6 +191,7 @@ struct solo_handle {
     bool opt_scan_pairs = false;  // solo_set_option("scan_pairs", 1): cta_group::2 list scan
     int opt_round0_scores = 4096;   // scores per query appended unconditionally by the first scan round
     bool opt_front_probes = true;   // probe selection writes the closest lists first
+    int opt_train_balance = 0;      // balancing rounds after the Lloyd iterations of ivf_train (0: plain Lloyd)
     bool opt_compact_probes = true; // thresholded coarse pass + compact probe selection (no (Q, nlist) score matrix)
     int64_t compact_probe_batches = 0;
     int opt_tc_nb = 0;              // > 0: rows of the resident list chunk of the tcgen05 scan (multiple of 32; tuning)
