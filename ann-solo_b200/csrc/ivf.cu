@@ -1668,7 +1668,7 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
         StageTimer t(h, ST_SCAN, 1, round == 0 ? scan_units : 0.0);
         if (use_tc) {
             launch_scan_tc(h, ix, sa.goff, sa.gq, qh.as<__half>(), qmask.as<uint32_t>(), q_scale_log2, sa.tau, sa.buf,
-                           sa.cnt, cap, tile_cnt, tile_off, items);
+                           sa.cnt, cap, tile_cnt, tile_off, items, round == 0);
         } else {
             scan_exact_kernel<<<dim3(nlist, ysplit), EN_WARPS * 32, en_smem, st>>>(sa);
             SOLO_CUDA(cudaGetLastError());

@@ -84,7 +84,7 @@ void tc_prepare_queries(solo_handle *h, const IvfIndex &ix, const float *q, int 
                         uint32_t *qmask);
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
                     const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
-                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items);
+                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items, bool dense_round = false);
 void ivf_set_centroids(solo_handle *h, IvfIndex &ix, const float *h_cent, int nlist, int dim);
 void ivf_add_device(solo_handle *h, IvfIndex &ix, const float *d_x, int64_t n, bool assign = true);  // d_x on device
 void ivf_train_rows(solo_handle *h, IvfIndex &ix, int64_t n, int dim, int nlist, int iters, uint64_t seed,

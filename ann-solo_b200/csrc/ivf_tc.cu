@@ -169,6 +169,7 @@ struct TcScanArgs {
     int dense_ld;
     unsigned long long *prof; // optional (SOLO_TC_PROF=1): per-CTA wait-cycle counters, 8 per CTA
     int debug;                // timing experiments only (SOLO_TC_DEBUG): 1 = skip query copies, 2 = skip score handling
+    int a_col0;               // scan_ts_kernel: first tensor-memory column of the resident list chunk (the accumulator sits in front)
 };
 
 // wait on an mbarrier; when profiling, add the cycles spent to *acc
@@ -1091,6 +1092,415 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
 }
 
 // only lists with len_lo < length <= len_hi take part (the scan may split the lists between two kernel variants)
+// ======================================================================= swapped operands (scan_ts_kernel)
+//
+// The list chunk is the A operand and lives in TENSOR MEMORY, the gathered query rows are the B operand.
+//   work item = chunk of <= 128 consecutive vectors of a list (one TMEM lane per vector, fp16 pairs packed into
+//               dim / 2 columns: 400 of the 512 columns at dim 800), written once per item by the epilogue warps
+//               (TMA box -> staging -> ld.shared -> tcgen05.st);
+//   tile      = NQ queries of the list's query group: NQ gathered fp16 rows per k-block are the B operand
+//               (N = NQ), streamed through a ring that has ALL of shared memory because no list chunk is resident
+//               there (14 stages of 12 KB instead of 4 of 16 KB: the gather's L2 latency, which bounds
+//               scan_tc_kernel's two-batch ring, is covered);
+//   D         = 128 lanes (list vectors) x NQ fp32 columns (queries), one accumulator in front of the A columns.
+// Shared-memory traffic per k-block drops from 44 KB (16 KB written + 16 + 12 KB read by the MMAs) to 24 KB.
+// Epilogue: thread = list vector, column = query; per column one ballot over the warp's 32 vectors, one atomic
+// reservation per (warp, query) with a hit and coalesced 8-byte stores.
+// Hand-over unit = TS_BATCH k-blocks: one full / empty barrier pair and one tcgen05.commit per batch.
+constexpr int TS_MT = 128;            // list vectors per item (MMA M)
+constexpr int TS_BATCH = 2;           // k-blocks per hand-over
+constexpr int TS_MAX_SLOTS = 8;       // batch slots in the ring (stages = slots * TS_BATCH)
+constexpr int TS_RING = 3;            // staging boxes (TC_BOX list rows x 128 B) per loader warp
+constexpr int TS_SBOX = TS_RING * (TS_MT / TC_BOX);
+constexpr int TS_BOX_BYTES = TC_BOX * 128;
+
+struct __align__(8) TsBarriers {
+    unsigned long long full_q[TS_MAX_SLOTS];
+    unsigned long long empty_q[TS_MAX_SLOTS];
+    unsigned long long stg_full[TS_SBOX];
+    unsigned long long stg_empty[TS_SBOX];
+    unsigned long long a_full[TC_MAX_KB];
+    unsigned long long tmem_full;
+    unsigned long long tmem_empty;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns <- 8 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint4 &v0, const uint4 &v1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v0.x),
+                 "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// NQ: queries per tile (MMA N; 96 or 112). Warps: 0..7 epilogue + tensor-memory loader (set = warp >> 2 owns the
+// columns [set NQ/2, (set + 1) NQ/2) of the accumulator; warps 0..3 also load the list chunk into tensor memory),
+// 8 TMA (staging boxes), 9 MMA issuer, 10..13 query gather.
+template <int NUM_KB, int NQ, bool DENSE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_vec, TcScanArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    constexpr int ST_BYTES = NQ * 128;       // one k-block of a query tile
+    constexpr int HALF = NQ / 2;             // accumulator columns per epilogue warp set
+    static_assert(NQ % 16 == 0 && HALF % 8 == 0 && HALF >= 32 && HALF <= 64, "unsupported tile width");
+    const int num_kb = NUM_KB > 0 ? NUM_KB : (a.dim + TC_BK - 1) / TC_BK;
+    const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
+    const int n_slots = a.stages / TS_BATCH;
+    unsigned char *sQ = tc_smem;
+    unsigned char *sStg = tc_smem + (size_t)a.stages * ST_BYTES;
+    TsBarriers *bars = reinterpret_cast<TsBarriers *>(sStg + TS_SBOX * TS_BOX_BYTES);
+    int32_t *s_qid = reinterpret_cast<int32_t *>(bars + 1);   // [8 warps][64]
+    float *s_thr = reinterpret_cast<float *>(s_qid + 8 * 64);  // [8 warps][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = (int)a.item_off[a.nlist];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_MAX_SLOTS; ++s) {
+            mbar_init(smem_u32(&bars->full_q[s]), TC_PRODUCERS);
+            mbar_init(smem_u32(&bars->empty_q[s]), 1);
+        }
+        for (int s = 0; s < TS_SBOX; ++s) {
+            mbar_init(smem_u32(&bars->stg_full[s]), 1);
+            mbar_init(smem_u32(&bars->stg_empty[s]), 1);
+        }
+        for (int kb = 0; kb < TC_MAX_KB; ++kb) mbar_init(smem_u32(&bars->a_full[kb]), 4);
+        mbar_init(smem_u32(&bars->tmem_full), 1);
+        mbar_init(smem_u32(&bars->tmem_empty), TC_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_a = tmem_base + (uint32_t)a.a_col0;
+
+    if (warp < TC_EPI_WARPS) {
+        // ================= epilogue + tensor-memory loader =================
+        const int set = warp >> 2, w4 = warp & 3;
+        const int row = w4 * 32 + lane;                       // list vector of this thread = TMEM lane
+        const uint32_t lane_addr = (uint32_t)(w4 * 32) << 16;
+        const float scale = 1.f / a.inv_scale;
+        int32_t *my_q = s_qid + warp * 64;
+        float *my_thr = s_thr + warp * 64;
+        uint32_t tile_n = 0, box_seq = 0;   // box_seq: staging boxes this warp has consumed
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x, NQ);
+        // query ids and (pre-scaled) thresholds of my columns live in shared memory (my_q / my_thr); lane l fetches
+        // those of columns l and 32 + l of the NEXT tile while the current one is handled (qn / tn)
+        const float nan_thr = __int_as_float(0x7fc00000);   // behind the group's end: nothing passes
+        int qn[2] = {-1, -1};
+        float tn[2] = {nan_thr, nan_thr};
+        auto fetch_q = [&](const TileCursor &c) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int j = hh * 32 + lane;
+                const int gi = c.qb * NQ + set * HALF + j;
+                qn[hh] = (j < HALF && gi < c.cur.G) ? a.gq[c.cur.g0 + gi] : -1;
+            }
+        };
+        auto fetch_thr = [&]() {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) tn[hh] = qn[hh] >= 0 ? a.tau[qn[hh]] * scale : nan_thr;
+        };
+        auto publish = [&]() {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+                if (hh * 32 + lane < HALF) {
+                    my_q[hh * 32 + lane] = qn[hh];
+                    my_thr[hh * 32 + lane] = tn[hh];
+                }
+            __syncwarp();
+        };
+        if (tc.valid) {
+            fetch_q(tc);
+            fetch_thr();
+            publish();
+        }
+        while (tc.valid) {
+            const TcItem it = tc.cur;
+            TileCursor nx = tc;
+            nx.advance();
+            if (set == 0 && tc.first_qb()) {
+                // the list chunk -> tensor memory (warps 0..3, one lane quarter each); every MMA of the previous item
+                // has retired (this warp passed the tmem_full wait of its last tile). Each warp has a private ring of
+                // TS_RING staging boxes: one producer and one consumer per barrier, always in step (a ring shared by
+                // warps that drift apart lets a fast warp's parity wait match the PREVIOUS phase of a slot).
+                const int nbox = (it.nv + TC_BOX - 1) / TC_BOX;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (w4 < nbox) {
+                        const uint32_t slot = (uint32_t)w4 * TS_RING + box_seq % TS_RING, ph = (box_seq / TS_RING) & 1u;
+                        ++box_seq;
+                        mbar_wait(smem_u32(&bars->stg_full[slot]), ph);
+                        const unsigned char *rowp = sStg + slot * TS_BOX_BYTES + lane * 128;
+                        const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint4 v0 = *reinterpret_cast<const uint4 *>(rowp + (((2 * ks) ^ (lane & 7)) << 4));
+                            const uint4 v1 = *reinterpret_cast<const uint4 *>(rowp + (((2 * ks + 1) ^ (lane & 7)) << 4));
+                            tc_st8(tmem_a + lane_addr + (uint32_t)(kb * 32 + ks * 8), v0, v1);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->stg_empty[slot]));
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[kb]));
+                }
+            }
+            mbar_wait(smem_u32(&bars->tmem_full), tile_n & 1u);
+            tc_fence_after();
+            const bool rows_here = w4 * 32 < it.nv;
+            uint32_t r[HALF];
+            if (rows_here) {
+                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(set * HALF);
+                tc_ld32(taddr, r);
+                if constexpr (HALF >= 48) tc_ld16(taddr + 32, r + 32);
+                if constexpr (HALF == 40) tc_ld8(taddr + 32, r + 32);
+                if constexpr (HALF == 56) tc_ld8(taddr + 48, r + 48);
+                if constexpr (HALF == 64) tc_ld16(taddr + 48, r + 48);
+                tc_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty));
+            if (nx.valid) fetch_q(nx);   // in flight during pass 1
+            const bool valid = row < it.nv;
+            const bool work = rows_here && !(a.debug & 2);
+            const unsigned long long pos = (unsigned long long)(uint32_t)(it.p0 + row);
+            if (DENSE) {
+                // round 0 (thresholds at -inf: every score is appended): three passes so that the buffer reservations of
+                // a tile are TWO warp-wide atomics (one lane per column): (1) hits per column, (2) reservations, (3) stores
+                int hits[2] = {0, 0};        // lane l: hits of columns l and 32 + l
+                if (work) {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const bool pass = valid && __uint_as_float(r[j]) >= my_thr[j];   // a NaN score never passes
+                        const int n = __popc(__ballot_sync(0xffffffffu, pass));
+                        if (lane == (j & 31)) hits[j >> 5] = n;
+                    }
+                }
+                int base[2] = {0, 0};
+                if (hits[0] > 0) base[0] = atomicAdd(&a.cnt[my_q[lane]], hits[0]);
+                if (hits[1] > 0) base[1] = atomicAdd(&a.cnt[my_q[32 + lane]], hits[1]);
+                if (nx.valid) fetch_thr();   // in flight during the reservations and pass 3
+                if (work && __any_sync(0xffffffffu, (hits[0] | hits[1]) != 0)) {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        const bool pass = valid && v >= my_thr[j];
+                        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                        const int slot = __shfl_sync(0xffffffffu, base[j >> 5], j & 31);
+                        if (pass) {
+                            const int p = slot + __popc(bal & ((1u << lane) - 1u));
+                            if (p < a.cap)
+                                a.buf[(int64_t)my_q[j] * a.cap + p] =
+                                    ((unsigned long long)__float_as_uint(v * a.inv_scale) << 32) | pos;
+                        }
+                    }
+                }
+            } else {
+                // later rounds: a few per cent of the scores pass; each thread handles its own hits (no warp collectives:
+                // a column without a hit costs a compare and a branch)
+                if (nx.valid) fetch_thr();
+                if (work && valid) {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (v >= my_thr[j]) {   // NaN threshold behind the group's end; a NaN score never passes
+                            const int q = my_q[j];
+                            const int p = atomicAdd(&a.cnt[q], 1);
+                            if (p < a.cap)
+                                a.buf[(int64_t)q * a.cap + p] = ((unsigned long long)__float_as_uint(v * a.inv_scale) << 32) | pos;
+                        }
+                    }
+                }
+            }
+            __syncwarp();   // every lane is done with my_q / my_thr of this tile
+            if (nx.valid) publish();
+            ++tile_n;
+            tc = nx;
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ================= TMA: the item's list chunk, box by box, into the staging ring =================
+        uint32_t sq[TS_MT / TC_BOX] = {0, 0, 0, 0};   // boxes issued so far per loader warp
+        TcItem it, nxt;
+        int item = blockIdx.x;
+        if (item < n_items) it = a.items[item];
+        for (; item < n_items; item += gridDim.x) {
+            if (item + (int)gridDim.x < n_items) nxt = a.items[item + gridDim.x];
+            const int nbox = (it.nv + TC_BOX - 1) / TC_BOX;
+            for (int kb = 0; kb < num_kb; ++kb) {
+#pragma unroll
+                for (int b = 0; b < TS_MT / TC_BOX; ++b) {
+                    if (b < nbox) {
+                        const uint32_t slot = (uint32_t)b * TS_RING + sq[b] % TS_RING, ph = (sq[b] / TS_RING) & 1u;
+                        ++sq[b];
+                        mbar_wait(smem_u32(&bars->stg_empty[slot]), ph ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t fb = smem_u32(&bars->stg_full[slot]);
+                            mbar_expect_tx(fb, (uint32_t)TS_BOX_BYTES);
+                            tma_load_2d(smem_u32(sStg + slot * TS_BOX_BYTES), &tmap_vec, kb * TC_BK, it.p0 + b * TC_BOX, fb);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            it = nxt;
+        }
+    } else if (warp == TC_EPI_WARPS + 1) {
+        // ================= MMA issuer =================
+        const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t q_base = smem_u32(sQ);
+        const uint32_t idesc = make_idesc_f16(NQ);
+        uint32_t slot = 0, phase = 0, tile_n = 0, item_n = 0;
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x, NQ);
+        while (tc.valid) {
+            mbar_wait(smem_u32(&bars->tmem_empty), (tile_n & 1u) ^ 1u);
+            tc_fence_after();
+            const bool first_qb = tc.first_qb();
+            for (int kb0 = 0; kb0 < num_kb; kb0 += TS_BATCH) {
+                const int n = min(TS_BATCH, num_kb - kb0);
+                if (first_qb)
+                    for (int j = 0; j < n; ++j) mbar_wait(smem_u32(&bars->a_full[kb0 + j]), item_n & 1u);
+                mbar_wait(smem_u32(&bars->full_q[slot]), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    if (!(a.debug & 16)) {
+#pragma unroll
+                        for (int j = 0; j < TS_BATCH; ++j) {
+                            if (j < n) {
+                                const int kb = kb0 + j;
+                                uint64_t bdesc = desc_hi | (uint64_t)(((q_base + (slot * TS_BATCH + j) * ST_BYTES) >> 4) & 0x3FFFu);
+                                const int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                                for (int ks = 0; ks < ksteps; ++ks) {
+                                    tc_mma_f16_ts(tmem_base, tmem_a + (uint32_t)(kb * 32 + ks * 8), bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+                                    bdesc += 2;
+                                }
+                            }
+                        }
+                    }
+                    tc_commit(smem_u32(&bars->empty_q[slot]));
+                    if (kb0 + n == num_kb) tc_commit(smem_u32(&bars->tmem_full));
+                }
+                __syncwarp();
+                if (++slot == (uint32_t)n_slots) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (tc.last_qb()) ++item_n;
+            ++tile_n;
+            tc.advance();
+        }
+    } else {
+        // ================= query gather: NQ rows x 128 B per k-block, TS_BATCH k-blocks per hand-over =================
+        const int p = threadIdx.x - (TC_EPI_WARPS + 2) * 32;
+        const int chunk = p & 7, rbase = p >> 3;
+        constexpr int RSTEP = TC_PRODUCERS / 8;   // 16
+        constexpr int NR = NQ / RSTEP;            // rows per thread
+        const uint32_t dst_off = (uint32_t)(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));
+        const uint32_t q_base = smem_u32(sQ);
+        const size_t row_bytes = (size_t)a.dim * sizeof(__half);
+        const unsigned char *qh_c = reinterpret_cast<const unsigned char *>(a.qh) + chunk * 16;
+        uint32_t slot = 0, phase = 0;
+        TileCursor tc;
+        tc.init(a.items, n_items, blockIdx.x, gridDim.x, NQ);
+        const unsigned char *src[NR];
+        uint32_t nz[NR];
+        auto fetch_rows = [&](const TileCursor &c, const unsigned char *(&s)[NR], uint32_t (&m)[NR]) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int gi = c.qb * NQ + rbase + RSTEP * i;
+                const bool real = gi < c.cur.G;
+                const int q = a.gq[c.cur.g0 + (real ? gi : 0)];
+                s[i] = qh_c + (size_t)q * row_bytes;
+                m[i] = real ? a.qmask[(size_t)q * 8 + chunk] : 0u;   // padding rows are zero-filled
+            }
+        };
+        if (tc.valid) fetch_rows(tc, src, nz);
+        while (tc.valid) {
+            TileCursor nx = tc;
+            nx.advance();
+            const unsigned char *src_n[NR];
+            uint32_t nz_n[NR];
+            const int n_rowgroups = (min(tc.cur.G - tc.qb * NQ, NQ) + RSTEP - 1) / RSTEP;
+            for (int kb0 = 0; kb0 < num_kb; kb0 += TS_BATCH) {
+                const int n = min(TS_BATCH, num_kb - kb0);
+                if (kb0 == 0 && nx.valid) fetch_rows(nx, src_n, nz_n);   // next tile's rows, one tile ahead
+                mbar_wait(smem_u32(&bars->empty_q[slot]), phase ^ 1u);
+                if (!(a.debug & 1)) {
+#pragma unroll
+                    for (int j = 0; j < TS_BATCH; ++j) {
+                        if (j < n) {
+                            const int kb = kb0 + j;
+                            const uint32_t dst0 = q_base + (slot * TS_BATCH + j) * ST_BYTES + dst_off;
+#pragma unroll
+                            for (int i = 0; i < NR; ++i)
+                                if (i < n_rowgroups)
+                                    cp_async16_zfill(dst0 + i * RSTEP * 128, src[i] + (size_t)kb * 128, (nz[i] >> kb) & 1u ? 16u : 0u);
+                        }
+                    }
+                }
+                cp_async_arrive_noinc(smem_u32(&bars->full_q[slot]));
+                if (++slot == (uint32_t)n_slots) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (nx.valid) {
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    src[i] = src_n[i];
+                    nz[i] = nz_n[i];
+                }
+            }
+            tc = nx;
+        }
+        cp_async_wait<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
 __global__ void tc_item_count_kernel(const int64_t *__restrict__ goff, const int64_t *__restrict__ list_off, int nlist,
                                      int nb, int64_t len_lo, int64_t len_hi, int32_t *__restrict__ cnt) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1341,12 +1751,79 @@ static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, cons
     tc_prof_report(h, "scan", kNumSMs);
 }
 
+// The swapped-operand scan (scan_ts_kernel): usable when the list chunk (dim / 2 columns) and an accumulator of at
+// least 96 columns fit the 512 columns of tensor memory.
+static int ts_tile_queries(const IvfIndex &ix, int want) {
+    const int a_cols = (ix.dim + 15) / 16 * 8;
+    if (ix.dim % 16 != 0) return 0;
+    if (want == 112 && a_cols + 112 <= 512) return 112;
+    return a_cols + 96 <= 512 ? 96 : 0;
+}
+
+static void scan_ts_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
+                         const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
+                         int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items, int nq_tile, bool dense) {
+    const int nlist = ix.nlist;
+    const int nb = TS_MT;
+    const int avail = TC_SMEM_MAX - 1024 - (int)sizeof(TsBarriers) - 8 * 64 * 8 - TS_SBOX * TS_BOX_BYTES;
+    int stages = avail / (nq_tile * 128) / TS_BATCH * TS_BATCH;
+    stages = std::min(stages, TS_MAX_SLOTS * TS_BATCH);
+    static const int env_st = getenv("SOLO_TS_STAGES") ? atoi(getenv("SOLO_TS_STAGES")) : 0;
+    if (env_st >= 2 * TS_BATCH && env_st <= stages) stages = env_st / TS_BATCH * TS_BATCH;
+    SOLO_REQUIRE(stages >= 2 * TS_BATCH, SOLO_ECAPACITY, "no room for the query ring of the swapped scan");
+    item_cnt.ensure((size_t)nlist * sizeof(int32_t));
+    item_off.ensure((size_t)(nlist + 1) * sizeof(int64_t));
+    items.ensure((size_t)(ix.nstored / nb + nlist + 1) * sizeof(TcItem));
+    const int64_t all = (int64_t)1 << 40;
+    tc_item_count_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(), nlist, nb, 0, all,
+                                                                    item_cnt.as<int32_t>());
+    scan_counts_i32(h, item_cnt.as<int32_t>(), nlist, item_off.as<int64_t>());
+    tc_item_fill_kernel<<<div_up(nlist, 256), 256, 0, h->stream>>>(goff, ix.list_off.as<int64_t>(),
+                                                                   item_off.as<int64_t>(), nlist, nb, items.as<TcItem>());
+    TcScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.items = items.as<TcItem>();
+    a.item_off = item_off.as<int64_t>();
+    a.gq = gq;
+    a.qh = qh;
+    a.qmask = qmask;
+    a.nlist = nlist;
+    a.dim = ix.dim;
+    a.nb = nb;
+    a.stages = stages;
+    a.inv_scale = ldexpf(1.f, -(ix.scale_log2 + q_scale_log2));
+    a.tau = tau;
+    a.buf = buf;
+    a.cnt = cnt;
+    a.cap = cap;
+    a.a_col0 = nq_tile;
+    static const int v_debug = getenv("SOLO_TC_DEBUG") ? atoi(getenv("SOLO_TC_DEBUG")) : 0;
+    a.debug = v_debug | h->opt_tc_debug;
+    const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
+    const size_t smem = (size_t)stages * nq_tile * 128 + (size_t)TS_SBOX * TS_BOX_BYTES + sizeof(TsBarriers) + 8 * 64 * 8 + 1024;
+    SOLO_REQUIRE(smem <= (size_t)TC_SMEM_MAX, SOLO_ECAPACITY, "swapped scan kernel needs %zu bytes of shared memory", smem);
+    CUtensorMap map;
+    memcpy(&map, ix.tmap_storage, sizeof map);
+    void (*kern)(const CUtensorMap, TcScanArgs) = nullptr;
+    if (nq_tile == 112) {
+        if (dense) kern = num_kb == 13 ? scan_ts_kernel<13, 112, true> : scan_ts_kernel<0, 112, true>;
+        else kern = num_kb == 13 ? scan_ts_kernel<13, 112, false> : scan_ts_kernel<0, 112, false>;
+    } else {
+        if (dense) kern = num_kb == 13 ? scan_ts_kernel<13, 96, true> : scan_ts_kernel<0, 96, true>;
+        else kern = num_kb == 13 ? scan_ts_kernel<13, 96, false> : scan_ts_kernel<0, 96, false>;
+    }
+    SOLO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<kNumSMs, TC_THREADS, smem, h->stream>>>(map, a);
+    SOLO_CUDA(cudaGetLastError());
+    h->launches += 3;
+}
+
 // K3 for one round. Lists up to `hybrid` vectors go through the resident-chunk kernel (<= 96-row chunks,
 // read once per item), longer lists through the streamed-chunk variant (up to 256 rows per MMA, the
 // chunk re-read from L2 per query block): fewer, larger tiles where the issue-bound pipeline pays most.
 void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
                     const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
-                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items) {
+                    int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items, bool dense_round) {
     SOLO_REQUIRE(ix.tmap_valid, SOLO_ESTATE, "tensor map missing");
     static const bool env_pairs = getenv("SOLO_TC_PAIRS") && atoi(getenv("SOLO_TC_PAIRS")) != 0;
     const bool pairs = h->opt_scan_pairs || env_pairs;
@@ -1355,6 +1832,13 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     static const int env_hybrid = getenv("SOLO_TC_HYBRID") ? atoi(getenv("SOLO_TC_HYBRID")) : -1;
     const int64_t hybrid = env_hybrid >= 0 ? env_hybrid : h->opt_scan_hybrid;
     const int64_t all = (int64_t)1 << 40;
+    static const int env_ts = getenv("SOLO_TC_TS") ? atoi(getenv("SOLO_TC_TS")) : -1;
+    const int ts = env_ts >= 0 ? env_ts : h->opt_scan_ts;   // 0: off, 96 / 112: queries per tile
+    const int nq_tile = (ts > 0 && !pairs && !wide) ? ts_tile_queries(ix, ts) : 0;
+    if (nq_tile > 0) {
+        scan_ts_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, nq_tile, dense_round);
+        return;
+    }
     if (pairs || wide || hybrid <= 0 || ix.max_list_len <= hybrid) {
         scan_tc_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, pairs, wide, 0,
                      all);

@@ -348,6 +348,11 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_hybrid = (int)value;
         } else if (strcmp(key, "scan_pairs") == 0) {
             h->opt_scan_pairs = value != 0;
+        } else if (strcmp(key, "tc_debug") == 0) {
+            h->opt_tc_debug = (int)value;
+        } else if (strcmp(key, "scan_ts") == 0) {
+            SOLO_REQUIRE(value == 0 || value == 96 || value == 112, SOLO_EINVAL, "scan_ts must be 0, 96 or 112");
+            h->opt_scan_ts = (int)value;
         } else if (strcmp(key, "front_probes") == 0) {
             h->opt_front_probes = value != 0;
         } else if (strcmp(key, "train_balance") == 0) {

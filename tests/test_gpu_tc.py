@@ -59,8 +59,16 @@ def test_topk_bit_exact_both_engines(engine, oracle, synth, n, nlist, nprobe, k,
             D, I = engine.ivf_search(CH, qv, k, nprobe)
             assert np.array_equal(I, Iw), f"engine {eng_id}"
             assert np.array_equal(D, Dw), f"engine {eng_id}"
+        # the swapped-operand scan (list chunk in tensor memory, scan_ts_kernel): 96 and 112 queries per tile
+        engine.set_option("scan_engine", 0)
+        for nq_tile in (96, 112):
+            engine.set_option("scan_ts", nq_tile)
+            D, I = engine.ivf_search(CH, qv, k, nprobe)
+            assert np.array_equal(I, Iw), f"scan_ts {nq_tile}"
+            assert np.array_equal(D, Dw), f"scan_ts {nq_tile}"
     finally:
         engine.set_option("scan_engine", 0)
+        engine.set_option("scan_ts", 0)
 
 
 def test_near_ties_are_resolved_exactly(engine, oracle, synth):
