@@ -474,7 +474,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
             // out together after its last MMA. This warp is the serial bottleneck of the kernel: with
             // NUM_KB fixed and a four-stage ring everything below unrolls into straight-line code
             // (stage = g & 3, phase = (g >> 2) & 1 for the running k-block counter g).
-            if (NUM_KB > 0 && n_stages == 4) {
+            if (NUM_KB > 0 && n_stages == 4 && !(a.debug & 256)) {
                 constexpr int KBB = 2;
                 constexpr int NKB = NUM_KB > 0 ? NUM_KB : 1;
 #pragma unroll
@@ -1720,7 +1720,8 @@ static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, cons
     a.dense_ld = 0;
     a.prof = tc_prof_buffer();
     static const int v_debug = getenv("SOLO_TC_DEBUG") ? atoi(getenv("SOLO_TC_DEBUG")) : 0;
-    a.debug = v_debug;
+    a.debug = v_debug | h->opt_tc_debug;
+    if (h->opt_tc_stages >= 2 && h->opt_tc_stages < stages && !pairs) a.stages = stages = h->opt_tc_stages;
     const int num_kb = (ix.dim + TC_BK - 1) / TC_BK;
     if (pairs) {
         const size_t smem2 = (size_t)stages * TC_A_BYTES + (size_t)num_kb * (nb / 2) * 128 + sizeof(Tc2Barriers) + 1024;

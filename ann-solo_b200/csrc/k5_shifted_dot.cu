@@ -201,7 +201,15 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_best_match_kernel(K5Params p
         const int z = p.lib_prec_z[row];
         const double delta = __dmul_rn(__dsub_rn(q_prec, p.lib_prec_mz[row]), (double)z);
         const int nshift = (p.allow_shift && fabs(delta) >= tol) ? z + 1 : 1;
-        const double md_lane = (lane > 0 && lane < nshift) ? __ddiv_rn(delta, (double)lane) : 0.0;
+        // delta / lane: lanes 1, 2 and 4 divide by a power of two (exact scaling, |delta| >= tol here, so no
+        // subnormals); only a lane 3, 5, 6 or 7 (precursor charge >= 3) runs the ~40-instruction double division
+        double md_lane = 0.0;
+        if (lane > 0 && lane < nshift) {
+            if (lane == 1) md_lane = delta;
+            else if (lane == 2) md_lane = __dmul_rn(delta, 0.5);
+            else if (lane == 4) md_lane = __dmul_rn(delta, 0.25);
+            else md_lane = __ddiv_rn(delta, (double)lane);
+        }
 
         if (n > 0) {
             for (int s = 0; s < nshift; ++s) {
@@ -409,6 +417,18 @@ struct K5FastWarpMem {
     float mdf[8];  // ... as float (bucket lookup only)
 };
 
+struct K5FastCtaMem {
+    K5FastWarpMem w[K5_WARPS];
+    double qmz[64];
+    double qthr[64];
+    double best_score[K5_WARPS];
+    float qtf[64];
+    float qint[64];
+    int best_pos[K5_WARPS];
+    int best_np[K5_WARPS];
+    int best_row[K5_WARPS];
+};
+
 __global__ void k5_build_meta_kernel(const int64_t *__restrict__ off, const double *__restrict__ prec_mz,
                                      const int32_t *__restrict__ prec_z, int64_t n, LibMeta *__restrict__ meta) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,16 +481,19 @@ struct K5FastParams {
 
 __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams fp) {
     const K5Params &p = fp.p;
+    // one block of dynamic shared memory for everything (per-warp areas, the query, the per-warp winners): every
+    // access is base register + immediate (separate static arrays cost an address computation per use)
     extern __shared__ __align__(16) unsigned char k5_smem[];
-    K5FastWarpMem *wm_all = reinterpret_cast<K5FastWarpMem *>(k5_smem);
-    __shared__ double s_qmz[64];
-    __shared__ double s_qthr[64];  // q_mz - tol (SpectrumMatch.cpp:41)
-    __shared__ float s_qtf[64];    // float copy of it minus the bucket safety margin
-    __shared__ float s_qint[64];
-    __shared__ double s_best_score[K5_WARPS];
-    __shared__ int s_best_pos[K5_WARPS];
-    __shared__ int s_best_np[K5_WARPS];
-    __shared__ int s_best_row[K5_WARPS];
+    K5FastCtaMem &cm = *reinterpret_cast<K5FastCtaMem *>(k5_smem);
+    K5FastWarpMem *wm_all = cm.w;
+    double (&s_qmz)[64] = cm.qmz;
+    double (&s_qthr)[64] = cm.qthr;  // q_mz - tol (SpectrumMatch.cpp:41)
+    float (&s_qtf)[64] = cm.qtf;     // float copy of it minus the bucket safety margin
+    float (&s_qint)[64] = cm.qint;
+    double (&s_best_score)[K5_WARPS] = cm.best_score;
+    int (&s_best_pos)[K5_WARPS] = cm.best_pos;
+    int (&s_best_np)[K5_WARPS] = cm.best_np;
+    int (&s_best_row)[K5_WARPS] = cm.best_row;
     constexpr int MAXR = K5_MAXM / 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -581,7 +604,15 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 3) k5_fast_kernel(K5FastParams 
         // SpectrumMatch.cpp:18-31
         const double delta = __dmul_rn(__dsub_rn(q_prec, c_prec), (double)z);
         const int nshift = (p.allow_shift && fabs(delta) >= tol) ? z + 1 : 1;
-        const double md_lane = (lane > 0 && lane < nshift) ? __ddiv_rn(delta, (double)lane) : 0.0;
+        // delta / lane: lanes 1, 2 and 4 divide by a power of two (exact scaling, |delta| >= tol here, so no
+        // subnormals); only a lane 3, 5, 6 or 7 (precursor charge >= 3) runs the ~40-instruction double division
+        double md_lane = 0.0;
+        if (lane > 0 && lane < nshift) {
+            if (lane == 1) md_lane = delta;
+            else if (lane == 2) md_lane = __dmul_rn(delta, 0.5);
+            else if (lane == 4) md_lane = __dmul_rn(delta, 0.25);
+            else md_lane = __ddiv_rn(delta, (double)lane);
+        }
         if (lane < 8) {
             wm.md[lane] = md_lane;
             wm.mdf[lane] = __double2float_rn(md_lane);
@@ -806,7 +837,7 @@ void launch_best_match(solo_handle *h, const ScoreArgs &a) {
         fp.table = L.table.as<uint8_t>();
         static const int v_dbg = getenv("SOLO_K5_DEBUG") ? atoi(getenv("SOLO_K5_DEBUG")) : 0;
         fp.debug = v_dbg;
-        const size_t smem = sizeof(K5FastWarpMem) * K5_WARPS;
+        const size_t smem = sizeof(K5FastCtaMem);
         SOLO_CUDA(cudaFuncSetAttribute(k5_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k5_fast_kernel<<<a.nq, K5_WARPS * 32, smem, h->stream>>>(fp);
         SOLO_CUDA(cudaGetLastError());
