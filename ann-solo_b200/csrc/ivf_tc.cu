@@ -1861,13 +1861,23 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
                       float *out, int ld, int n_lists, const float *tau, unsigned long long *buf, int32_t *cnt, int cap) {
     SOLO_REQUIRE(ix.tmap_cent_valid, SOLO_ESTATE, "centroid tensor map missing");
     int nb, stages;
-    tc_smem_plan(ix, &nb, &stages, 64);  // every centroid chunk sees every query: short chunks, deep query ring
+    // 96-centroid chunks and the four-stage ring (the straight-line MMA issue path of scan_tc_kernel); every item is
+    // one chunk x one span of 512 queries, so that the (chunk, span) items spread evenly over the SMs (171 chunks
+    // of the 16,384 centroids alone would leave 23 SMs with twice the work of the others)
+    static const int env_cnb = getenv("SOLO_COARSE_NB") ? atoi(getenv("SOLO_COARSE_NB")) : 96;
+    // (the sampled prefix keeps 64-centroid chunks: its dense output rows are exactly n_lists wide)
+    int nb_full, st_full, nb_pref, st_pref;
+    tc_smem_plan(ix, &nb_full, &st_full, env_cnb);
+    tc_smem_plan(ix, &nb_pref, &st_pref, 64);
+    nb = n_lists < 0 ? nb_full : nb_pref;
+    stages = n_lists < 0 ? st_full : st_pref;
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
-    const int n_items = div_up(ix.nlist, nb);
-    // the sampled prefix is only a few chunks: its items also split the query range (512 queries each) so that
-    // the pass still fills the machine; they are stored behind the full-table items
-    const int n_pref_chunks = n_lists < 0 ? std::max(ix.coarse_items_used, 0) : std::min(n_items, div_up(n_lists, nb));
+    SOLO_REQUIRE(n_lists < 0 || n_lists % nb_pref == 0 || n_lists >= ix.nlist, SOLO_EINVAL, "coarse prefix must be a multiple of %d centroids", nb_pref);
+    const int n_chunks = div_up(ix.nlist, nb_full);
+    const int n_pref_chunks =
+        n_lists < 0 ? std::max(ix.coarse_items_used, 0) : std::min(div_up(ix.nlist, nb_pref), div_up(n_lists, nb_pref));
     const int q_span = 4 * TC_BM, n_spans = div_up(nq, q_span);
+    const int n_items = n_chunks * n_spans;
     const int n_used = n_pref_chunks * n_spans;
     constexpr int HDR = 4;  // int64 header: [0, items of the full table | 0, items of the sampled prefix]
     if (ix.coarse_items_nq != nq || (n_lists >= 0 && ix.coarse_items_used != n_pref_chunks)) {  // tiny: built on the host, cached
@@ -1878,20 +1888,18 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
         hoff[2] = 0;
         hoff[3] = n_used;
         TcItem *hit = reinterpret_cast<TcItem *>(hbuf.data() + HDR * sizeof(int64_t));
-        for (int i = 0; i < n_items; ++i) {
-            hit[i].p0 = i * nb;
-            hit[i].nv = std::min(nb, ix.nlist - i * nb);
-            hit[i].g0 = 0;
-            hit[i].G = nq;
-        }
-        for (int c = 0; c < n_pref_chunks; ++c)
-            for (int sp = 0; sp < n_spans; ++sp) {
-                TcItem &t = hit[n_items + c * n_spans + sp];
-                t.p0 = c * nb;
-                t.nv = std::min(nb, ix.nlist - c * nb);
-                t.g0 = sp * q_span;
-                t.G = std::min(q_span, nq - sp * q_span);
-            }
+        auto fill = [&](TcItem *dst, int chunks, int rows) {
+            for (int c = 0; c < chunks; ++c)
+                for (int sp = 0; sp < n_spans; ++sp) {
+                    TcItem &t = dst[c * n_spans + sp];
+                    t.p0 = c * rows;
+                    t.nv = std::min(rows, ix.nlist - c * rows);
+                    t.g0 = sp * q_span;
+                    t.G = std::min(q_span, nq - sp * q_span);
+                }
+        };
+        fill(hit, n_chunks, nb_full);
+        fill(hit + n_items, n_pref_chunks, nb_pref);
         SOLO_CUDA(cudaStreamSynchronize(h->stream));  // earlier launches may still read the old descriptors
         ix.coarse_items.ensure(hbuf.size());
         SOLO_CUDA(cudaMemcpy(ix.coarse_items.p, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice));
@@ -1941,12 +1949,12 @@ void launch_coarse_tc(solo_handle *h, IvfIndex &ix, const __half *qh, const uint
     (void)n_pref_chunks;
     SOLO_CUDA(cudaGetLastError());
     h->launches += 1;
-    tc_prof_report(h, "coarse", std::min(kNumSMs, n_items));
+    tc_prof_report(h, "coarse", std::min(kNumSMs, n_lists < 0 ? n_items : n_used));
 }
 
 // Fall-back of the compact probe selection: dense coarse scores for the queries of a device-side list (n_fail of
 // them, known only on the device: the items are rewritten there, no host round trip). Rows land at out[q * ld].
-__global__ void coarse_fallback_items_kernel(const TcItem *__restrict__ src, int n_items, const int32_t *__restrict__ n_fail,
+__global__ void coarse_fallback_items_kernel(int nlist, int nb, int n_items, const int32_t *__restrict__ n_fail,
                                              TcItem *__restrict__ dst, int64_t *__restrict__ hdr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nf = *n_fail;
@@ -1954,8 +1962,11 @@ __global__ void coarse_fallback_items_kernel(const TcItem *__restrict__ src, int
         hdr[0] = 0;
         hdr[1] = nf > 0 ? n_items : 0;
     }
-    if (i < n_items) {
-        TcItem it = src[i];
+    if (i < n_items) {   // centroid chunk i against the listed queries
+        TcItem it;
+        it.p0 = i * nb;
+        it.nv = min(nb, nlist - i * nb);
+        it.g0 = 0;
         it.G = nf;
         dst[i] = it;
     }
@@ -1967,13 +1978,11 @@ void launch_coarse_tc_listed(solo_handle *h, IvfIndex &ix, const __half *qh, con
     int nb, stages;
     tc_smem_plan(ix, &nb, &stages, 64);
     const int n_items = div_up(ix.nlist, nb);
-    constexpr int HDR = 4;
     DevBuf &fb = ix.coarse_fb_items;
     fb.ensure(2 * sizeof(int64_t) + (size_t)n_items * sizeof(TcItem));
     TcItem *fb_items = reinterpret_cast<TcItem *>(fb.as<unsigned char>() + 2 * sizeof(int64_t));
-    coarse_fallback_items_kernel<<<div_up(n_items, 256), 256, 0, h->stream>>>(
-        reinterpret_cast<const TcItem *>(ix.coarse_items.as<unsigned char>() + HDR * sizeof(int64_t)), n_items, n_listed,
-        fb_items, fb.as<int64_t>());
+    coarse_fallback_items_kernel<<<div_up(n_items, 256), 256, 0, h->stream>>>(ix.nlist, nb, n_items, n_listed, fb_items,
+                                                                              fb.as<int64_t>());
     TcScanArgs a;
     memset(&a, 0, sizeof a);
     a.items = fb_items;
