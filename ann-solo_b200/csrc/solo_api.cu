@@ -348,6 +348,8 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_hybrid = (int)value;
         } else if (strcmp(key, "scan_pairs") == 0) {
             h->opt_scan_pairs = value != 0;
+        } else if (strcmp(key, "sort_items") == 0) {
+            h->opt_sort_items = value != 0;
         } else if (strcmp(key, "tc_stages") == 0) {
             h->opt_tc_stages = (int)value;
         } else if (strcmp(key, "tc_debug") == 0) {
