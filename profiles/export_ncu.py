@@ -50,8 +50,8 @@ def main():
 
     acc = {}
     for r in data:
-        name = re.sub(r"[<(].*", "", r[hi["Kernel Name"]])
-        full = r[hi["Kernel Name"]]
+        full = re.sub(r"^void\s+", "", r[hi["Kernel Name"]])
+        name = re.sub(r"[<(].*", "", full)
         key = name
         if name == "scan_tc_kernel":
             key = "k2_coarse" if re.search(r"scan_tc_kernel<\(int\)1|scan_tc_kernel<1", full) or ", 7>" in full or "(int)7>" in full else "k3_list_scan"
