@@ -1531,6 +1531,12 @@ __global__ void tc_item_fill_kernel(const int64_t *__restrict__ goff, const int6
 // Items ordered by their number of query tiles, largest first (counting sort, one CTA): the persistent CTAs take
 // items b, b + gridDim.x, ... so every "row" of gridDim.x consecutive sorted items costs each CTA about the same and the
 // per-CTA totals end up within a tile or two of each other (list order left up to 23 % between the mean and the slowest CTA).
+// cost estimate of an item in quarter tiles: the query tiles plus the chunk load (up to one tile's worth for a full
+// chunk: what separates the single-tile items of the first round)
+__device__ __forceinline__ int tc_item_cost(const TcItem &it, int bm, int nbin) {
+    return min(nbin - 1, 4 * ((it.G + bm - 1) / bm) + (it.nv + 31) / 32);
+}
+
 __global__ void __launch_bounds__(1024) tc_item_sort_kernel(const TcItem *__restrict__ in, const int64_t *__restrict__ n_ptr,
                                                            TcItem *__restrict__ out, int bm) {
     constexpr int NBIN = 256;
@@ -1539,8 +1545,8 @@ __global__ void __launch_bounds__(1024) tc_item_sort_kernel(const TcItem *__rest
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int t = min(NBIN - 1, (in[i].G + bm - 1) / bm);
-        atomicAdd(&s_cnt[NBIN - 1 - t], 1);   // bin 0 = the most tiles
+        const int t = tc_item_cost(in[i], bm, NBIN);
+        atomicAdd(&s_cnt[NBIN - 1 - t], 1);   // bin 0 = the most expensive items
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1553,7 +1559,7 @@ __global__ void __launch_bounds__(1024) tc_item_sort_kernel(const TcItem *__rest
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const TcItem it = in[i];
-        const int t = min(NBIN - 1, (it.G + bm - 1) / bm);
+        const int t = tc_item_cost(it, bm, NBIN);
         out[atomicAdd(&s_off[NBIN - 1 - t], 1)] = it;
     }
 }
@@ -1712,12 +1718,12 @@ static void tc2_smem_plan(const IvfIndex &ix, int *nb_out, int *stages_out) {
 static void scan_tc_pass(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int32_t *gq, const __half *qh,
                          const uint32_t *qmask, int q_scale_log2, const float *tau, unsigned long long *buf, int32_t *cnt,
                          int cap, DevBuf &item_cnt, DevBuf &item_off, DevBuf &items, bool pairs, bool wide, int64_t len_lo,
-                         int64_t len_hi) {
+                         int64_t len_hi, int wide_nb = 0) {
     const int nlist = ix.nlist;
     int nb, stages;
     if (pairs) tc2_smem_plan(ix, &nb, &stages);
     else if (wide) {
-        nb = h->opt_tc_nb >= 32 ? h->opt_tc_nb : 256;
+        nb = wide_nb >= 32 ? wide_nb : (h->opt_tc_nb >= 32 ? h->opt_tc_nb : 256);
         stages = std::min((TC_SMEM_MAX - 1024 - (int)sizeof(TcBarriers) - 64) / (TC_A_BYTES + nb * 128), TC_MAX_STAGES);
     } else tc_smem_plan(ix, &nb, &stages, 256, h->opt_tc_nb);
     SOLO_REQUIRE(nb >= 32 && stages >= 2, SOLO_ECAPACITY, "dim %d too large for the tensor-core scan", ix.dim);
@@ -1875,6 +1881,14 @@ void launch_scan_tc(solo_handle *h, IvfIndex &ix, const int64_t *goff, const int
     const int nq_tile = (ts > 0 && !pairs && !wide) ? ts_tile_queries(ix, ts) : 0;
     if (nq_tile > 0) {
         scan_ts_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, nq_tile, dense_round);
+        return;
+    }
+    if (dense_round && h->opt_round0_wide > 0 && !pairs && !wide) {
+        // first round: every item is a single tile of a few queries, its list chunk is used once. Streaming the chunk
+        // through the ring next to the query stage keeps the loads of the following items in flight (the resident
+        // layout looks one item ahead only, and the chunk comes from DRAM)
+        scan_tc_pass(h, ix, goff, gq, qh, qmask, q_scale_log2, tau, buf, cnt, cap, item_cnt, item_off, items, false, true, 0,
+                     all, h->opt_round0_wide);
         return;
     }
     if (pairs || wide || hybrid <= 0 || ix.max_list_len <= hybrid) {

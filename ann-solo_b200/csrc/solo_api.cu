@@ -348,6 +348,9 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
             h->opt_scan_hybrid = (int)value;
         } else if (strcmp(key, "scan_pairs") == 0) {
             h->opt_scan_pairs = value != 0;
+        } else if (strcmp(key, "round0_wide") == 0) {
+            SOLO_REQUIRE(value >= 0 && value <= 256 && value % 32 == 0, SOLO_EINVAL, "round0_wide must be a multiple of 32 in [0, 256]");
+            h->opt_round0_wide = (int)value;
         } else if (strcmp(key, "sort_items") == 0) {
             h->opt_sort_items = value != 0;
         } else if (strcmp(key, "tc_stages") == 0) {

@@ -189,6 +189,7 @@ struct solo_handle {
     bool opt_scan_wide = false;   // solo_set_option("scan_wide", 1): list vectors streamed per tile, chunks of up to 256 rows
     int opt_scan_hybrid = 0;      // > 0: lists longer than this use the streamed-chunk scan variant
     int opt_scan_ts = 0;          // solo_set_option("scan_ts", 96 | 112): swapped-operand list scan (list chunk in tensor memory), queries per tile
+    int opt_round0_wide = 0;      // > 0: the first scan round streams list chunks of this many rows through the ring
     bool opt_sort_items = true;   // scan items ordered by their tile count, largest first (balance over the persistent CTAs)
     int opt_tc_stages = 0;        // > 0: cap on the query stages of scan_tc_kernel (tuning)
     int opt_tc_debug = 0;         // timing experiments only (solo_set_option("tc_debug", bits)): see TcScanArgs::debug
