@@ -459,7 +459,8 @@ def run_stream(args, wl, rank, world, local_rank):
         # results of the (last) level to rank 0: one padded device tensor per field
         for key, tail, dt in out_fields:
             tdt = getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))
-            loc = torch.zeros((n_max,) + tail, dtype=tdt, device="cuda")
+            # (padding rows behind a rank's own count read "no match")
+            loc = torch.full((n_max,) + tail, -1 if key == "best_row" else 0, dtype=tdt, device="cuda")
             host = np.concatenate([o[key] for _, _, o in batches]) if batches else np.zeros((0,) + tail, dt)
             loc[:len(host)].copy_(torch.from_numpy(host.view(np.dtype(dt).name.replace("uint32", "int32"))), non_blocking=True)
             parts = [torch.empty_like(loc) for _ in range(world)] if rank == 0 else None
