@@ -627,10 +627,24 @@ __global__ void __launch_bounds__(256) select_probes_compact_kernel(CompactSelec
         return;
     }
     const unsigned long long *row = ca.cbuf + (int64_t)q * ca.cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long e = row[i];
-        s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(e >> 32)));
-        s_ids[i] = (uint32_t)(e & 0xFFFFFFFFull);
+    {   // four loads in flight per thread (n is about 1.8 nprobe: seven 8-byte loads per thread otherwise one by one)
+        const int step = blockDim.x;
+        int i = threadIdx.x;
+        for (; i + 3 * step < n; i += 4 * step) {
+            unsigned long long e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = row[i + u * step];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s_keys[i + u * step] = ivf_f2o(__uint_as_float((uint32_t)(e[u] >> 32)));
+                s_ids[i + u * step] = (uint32_t)(e[u] & 0xFFFFFFFFull);
+            }
+        }
+        for (; i < n; i += step) {
+            const unsigned long long e = row[i];
+            s_keys[i] = ivf_f2o(__uint_as_float((uint32_t)(e >> 32)));
+            s_ids[i] = (uint32_t)(e & 0xFFFFFFFFull);
+        }
     }
     if (threadIdx.x == 0) {
         s_cnt = 0;
