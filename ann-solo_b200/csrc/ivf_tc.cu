@@ -486,9 +486,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                     for (int j = 0; j < KBB; ++j) {
                         if (j < nkb) {
                             const uint32_t gj = g + (uint32_t)j;
-                            if (wide) mbar_wait_prof(smem_u32(&bars->full_b[gj & 3u]), (gj >> 2) & 1u, prof_on, pw1);
-                            else if (first_qb) mbar_wait_prof(smem_u32(&bars->full_b[kb0 + j]), n_local & 1, prof_on, pw1);
-                            if (j > 0 || !ready) mbar_wait_prof(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u, prof_on, pw2);
+                            if (wide) mbar_wait(smem_u32(&bars->full_b[gj & 3u]), (gj >> 2) & 1u);
+                            else if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb0 + j]), n_local & 1);
+                            if (j > 0 || !ready) mbar_wait(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u);
                         }
                     }
                     const uint32_t gn = g + (uint32_t)nkb;
