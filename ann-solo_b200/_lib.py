@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsolo_b200.so")
+LIB_PATH = os.environ.get("SOLO_LIB_PATH") or os.path.join(_HERE, "libsolo_b200.so")  # (override: build-variant experiments)
 
 SOLO_OK, SOLO_EINVAL, SOLO_ECUDA, SOLO_ENOMEM, SOLO_ESTATE, SOLO_ECAPACITY = 0, -1, -2, -3, -4, -5
 TOL_DA, TOL_PPM = 0, 1

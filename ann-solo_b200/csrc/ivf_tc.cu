@@ -18,15 +18,27 @@
 
 #include "ivf.cuh"
 
+// unroll factors of the two straight-line loops of scan_tc_kernel (the kernel is sensitive to its code size)
+#ifndef K3_UNROLL_MMA
+#define K3_UNROLL_MMA 1
+#endif
+#ifndef K3_UNROLL_PROD
+#define K3_UNROLL_PROD 13
+#endif
+
 namespace solo {
 
+constexpr int K3_UM = K3_UNROLL_MMA, K3_UP = K3_UNROLL_PROD;
 constexpr int TC_BM = 128;       // queries per accumulator tile (MMA M)
 constexpr int TC_BK = 64;        // fp16 elements per k-block = 128 bytes = one swizzle atom row
 constexpr int TC_MAX_STAGES = 12; // A (query) stages: as many as fit next to the resident list chunk
 constexpr int TC_BOX = 32;       // rows per TMA box
 constexpr int TC_A_BYTES = TC_BM * 128;
 constexpr int TC_MAX_KB = 24;    // dim <= 1536
-constexpr int TC_PRODUCERS = 128;  // A-producer threads (warps 6..)
+#ifndef K3_PRODUCERS
+#define K3_PRODUCERS 128
+#endif
+constexpr int TC_PRODUCERS = K3_PRODUCERS;  // A-producer threads (warps 10..)
 constexpr int TC_EPI_WARPS = 8;   // two sets of four: set s drains accumulator buffer s
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32 + TC_PRODUCERS;
 constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
@@ -69,6 +81,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
+}
+// two probes in flight together (each costs ~90 cycles until its predicate can be read)
+__device__ __forceinline__ void mbar_try_wait2(uint32_t bar0, uint32_t par0, uint32_t bar1, uint32_t par1, bool &ok0, bool &ok1) {
+    uint32_t r0, r1;
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p0, [%2], %3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p1, [%4], %5;\n"
+        "selp.u32 %0, 1, 0, p0;\n"
+        "selp.u32 %1, 1, 0, p1;\n"
+        "}\n"
+        : "=r"(r0), "=r"(r1)
+        : "r"(bar0), "r"(par0), "r"(bar1), "r"(par1)
+        : "memory");
+    ok0 = r0 != 0;
+    ok1 = r1 != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -456,7 +485,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         uint32_t stage = 0, phase = 0, unit = 0, n_local = 0;
         unsigned long long pq0 = 0, pq1 = 0, pq2 = 0;
-        bool ready = false;  // outcome of the early probe of full_a[stage]
+        bool ready = false, ready1 = false;  // outcome of the early probes of the next batch's query stages
         uint32_t g = 0;      // running k-block counter (straight-line path)
         const int kbb = max(1, min(a.kbb, n_stages / 2));  // k-blocks per issue batch
         const int last_ksteps = (a.dim - (num_kb - 1) * TC_BK) / 16;
@@ -477,7 +506,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
             if (NUM_KB > 0 && n_stages == 4 && !(a.debug & 256)) {
                 constexpr int KBB = 2;
                 constexpr int NKB = NUM_KB > 0 ? NUM_KB : 1;
-#pragma unroll
+#pragma unroll K3_UM
                 for (int kb0 = 0; kb0 < NKB; kb0 += KBB) {
                     constexpr int dummy = 0;
                     (void)dummy;
@@ -488,11 +517,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                             const uint32_t gj = g + (uint32_t)j;
                             if (wide) mbar_wait(smem_u32(&bars->full_b[gj & 3u]), (gj >> 2) & 1u);
                             else if (first_qb) mbar_wait(smem_u32(&bars->full_b[kb0 + j]), n_local & 1);
-                            if (j > 0 || !ready) mbar_wait(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u);
+                            // both query stages of the batch were probed behind the previous batch's commits (below):
+                            // when the gather is ahead nothing is waited for here
+                            if (!(j == 0 ? ready : ready1)) mbar_wait(smem_u32(&bars->full_a[gj & 3u]), (gj >> 2) & 1u);
                         }
                     }
                     const uint32_t gn = g + (uint32_t)nkb;
-                    const bool ready_next = mbar_try_wait(smem_u32(&bars->full_a[gn & 3u]), (gn >> 2) & 1u);
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -521,8 +551,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                         if (kb0 + nkb == NKB) tc_commit(smem_u32(&bars->tmem_full[buf]));
                     }
                     __syncwarp();
+                    // the next batch's stages, probed while the pipe works on this one
+                    mbar_try_wait2(smem_u32(&bars->full_a[gn & 3u]), (gn >> 2) & 1u, smem_u32(&bars->full_a[(gn + 1u) & 3u]),
+                                   ((gn + 1u) >> 2) & 1u, ready, ready1);
                     g = gn;
-                    ready = ready_next;
                 }
                 stage = g & 3u;
                 phase = (g >> 2) & 1u;
@@ -708,7 +740,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_vec, const __grid_consta
                 }
             };
             if (NUM_KB > 0) {
-#pragma unroll
+#pragma unroll K3_UP
                 for (int kb = 0; kb < NUM_KB; ++kb) produce(kb);
             } else {
                 for (int kb = 0; kb < num_kb; ++kb) produce(kb);
