@@ -3,7 +3,7 @@
 # the hot kernels of charge 2, and a compute-sanitizer pass over the tiny workload. Everything lands in gpurun_out/;
 # profiles/export_ncu.py turns the .ncu-rep files into the CSVs / traffic.json that are committed.
 #   gpurun --timeout 1500 -- 'bash profiles/profile.sh r2'
-TAG=${1:-r2b}
+TAG=${1:-r2c}
 OUT=gpurun_out
 mkdir -p $OUT
 export SOLO_NCU=1
