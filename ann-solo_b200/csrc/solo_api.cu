@@ -13,6 +13,9 @@ static thread_local std::string g_create_error;
 
 static const char *kStageNames[ST_COUNT] = {"vectorize", "coarse", "probe_select", "group", "scan",
                                             "topk",      "candidates", "score", "h2d", "d2h"};
+namespace solo {
+const char *stage_name(int st) { return st >= 0 && st < ST_COUNT ? kStageNames[st] : ""; }
+}  // namespace solo
 
 // ---------------------------------------------------------------- host helpers
 
@@ -351,6 +354,8 @@ int solo_set_option(solo_handle *h, const char *key, int64_t value) {
         } else if (strcmp(key, "round0_wide") == 0) {
             SOLO_REQUIRE(value >= 0 && value <= 256 && value % 32 == 0, SOLO_EINVAL, "round0_wide must be a multiple of 32 in [0, 256]");
             h->opt_round0_wide = (int)value;
+        } else if (strcmp(key, "nvtx") == 0) {
+            h->opt_nvtx = value != 0;
         } else if (strcmp(key, "sort_items") == 0) {
             h->opt_sort_items = value != 0;
         } else if (strcmp(key, "tc_stages") == 0) {

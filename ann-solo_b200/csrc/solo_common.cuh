@@ -1,5 +1,6 @@
 // Shared host/device declarations for libsolo_b200.so (sm_100a only).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -190,6 +191,7 @@ struct solo_handle {
     int opt_scan_hybrid = 0;      // > 0: lists longer than this use the streamed-chunk scan variant
     int opt_scan_ts = 0;          // solo_set_option("scan_ts", 96 | 112): swapped-operand list scan (list chunk in tensor memory), queries per tile
     int opt_round0_wide = 0;      // > 0: the first scan round streams list chunks of this many rows through the ring
+    bool opt_nvtx = getenv("SOLO_NVTX") != nullptr && getenv("SOLO_NVTX")[0] == '1';   // NVTX range per stage
     bool opt_sort_items = true;   // scan items ordered by their tile count, largest first (balance over the persistent CTAs)
     int opt_tc_stages = 0;        // > 0: cap on the query stages of scan_tc_kernel (tuning)
     int opt_tc_debug = 0;         // timing experiments only (solo_set_option("tc_debug", bits)): see TcScanArgs::debug
@@ -249,12 +251,20 @@ struct solo_handle {
 namespace solo {
 
 // RAII stage timer: records CUDA events around a stage when profiling is enabled.
+// NVTX ranges around the stages (SOLO_NVTX=1 or solo_set_option("nvtx", 1)): nvtx3 is header-only, the ranges cost nothing
+// unless a tool is attached
+const char *stage_name(int st);
 struct StageTimer {
     solo_handle *h;
     int st;
     cudaEvent_t a = nullptr, b = nullptr;
+    bool range = false;
     StageTimer(solo_handle *h_, int st_, int64_t launches, double units = 0.0, bool enabled = true) : h(h_), st(st_) {
         if (!enabled) return;
+        if (h->opt_nvtx) {
+            nvtxRangePushA(stage_name(st));
+            range = true;
+        }
         h->launches += launches;
         h->prof[st].launches += launches;
         h->prof[st].units += units;
@@ -269,6 +279,7 @@ struct StageTimer {
             cudaEventRecord(b, h->stream);
             h->prof[st].pending.emplace_back(a, b);
         }
+        if (range) nvtxRangePop();
     }
 };
 
