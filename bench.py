@@ -449,6 +449,31 @@ def run_stream(args, wl, rank, world, local_rank):
         n_max = int(t.item())
     gathered = {}
 
+    pinned_gather = {}
+
+    def gather_to_rank0():
+        # results of the (last) level to rank 0: one padded device tensor per field, gathered over NCCL, landed in
+        # pinned host memory on rank 0
+        for key, tail, dt in out_fields:
+            tdt = getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))
+            # (padding rows behind a rank's own count read "no match")
+            loc = torch.full((n_max,) + tail, -1 if key == "best_row" else 0, dtype=tdt, device="cuda")
+            off = 0
+            for _, _, o in batches:   # pinned result buffers -> device, asynchronously
+                t = torch.from_numpy(o[key].view(np.dtype(dt).name.replace("uint32", "int32")))
+                loc[off:off + len(t)].copy_(t, non_blocking=True)
+                off += len(t)
+            parts = [torch.empty_like(loc) for _ in range(world)] if rank == 0 else None
+            dist.gather(loc, parts, dst=0)
+            if rank == 0:
+                if key not in pinned_gather:
+                    pinned_gather[key] = torch.empty((world, n_max) + tail, dtype=tdt).pin_memory()
+                for r in range(world):
+                    pinned_gather[key][r].copy_(parts[r], non_blocking=True)
+        torch.cuda.synchronize()
+        if rank == 0:
+            gathered.update(pinned_gather)
+
     def one_pass(sel=None):
         todo = batches if sel is None else batches[:sel]
         for lv in levels:
@@ -456,21 +481,13 @@ def run_stream(args, wl, rank, world, local_rank):
                 pass
         if dist is None or sel is not None:
             return
-        # results of the (last) level to rank 0: one padded device tensor per field
-        for key, tail, dt in out_fields:
-            tdt = getattr(torch, np.dtype(dt).name.replace("uint32", "int32"))
-            # (padding rows behind a rank's own count read "no match")
-            loc = torch.full((n_max,) + tail, -1 if key == "best_row" else 0, dtype=tdt, device="cuda")
-            host = np.concatenate([o[key] for _, _, o in batches]) if batches else np.zeros((0,) + tail, dt)
-            loc[:len(host)].copy_(torch.from_numpy(host.view(np.dtype(dt).name.replace("uint32", "int32"))), non_blocking=True)
-            parts = [torch.empty_like(loc) for _ in range(world)] if rank == 0 else None
-            dist.gather(loc, parts, dst=0)
-            if rank == 0:
-                gathered[key] = torch.stack(parts).cpu()
+        gather_to_rank0()
 
     one_pass(sel=min(6, len(batches)))     # warm-up on a few batches of the stream (buffers, slots, lazy module loads)
     for _ in range(max(0, args.warmup - 1)):
         one_pass(sel=min(6, len(batches)))
+    if dist is not None:
+        gather_to_rank0()   # warm-up of the collective too (NCCL sets its point-to-point channels up on first use)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
