@@ -8,7 +8,7 @@ namespace solo {
 
 constexpr int IVF_MAX_K = 2048;        // top-k rows returned per query
 constexpr int IVF_MAX_NLIST = 32768;   // coarse scores of one query are selected in shared memory
-constexpr int64_t IVF_ROUND0_SCORES = 12288;  // scores per query appended unconditionally by scan round 0
+constexpr int64_t IVF_ROUND0_SCORES = 24576;  // longest inverted list: round 0 appends a whole list unconditionally and the per-query buffer holds 32,768 entries
 constexpr unsigned long long IVF_PACKED_PAD = 0xFF800000FFFFFFFFull;  // score -inf, row -1
 constexpr float IVF_REL_EPS = 1.25e-3f;  // bound on |approx - exact| / sum|q_d c_d| for the fp16 tensor path
 

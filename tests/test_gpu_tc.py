@@ -71,6 +71,23 @@ def test_topk_bit_exact_both_engines(engine, oracle, synth, n, nlist, nprobe, k,
         engine.set_option("scan_ts", 0)
 
 
+def test_lists_of_twenty_thousand_vectors(engine, oracle, synth):
+    """Inverted lists far beyond the 96-row chunk and beyond the former 12,288-vector cap (C5-sized lists): many chunks
+    per list, a first scan round that appends a whole 20 k-vector list, the large-capacity top-k launch."""
+    n, nlist, nprobe, k, nq = 60000, 3, 2, 1024, 48
+    lib, x, cent = _index(engine, oracle, synth, n, nlist, seed=141)
+    q = synth.make_queries(lib, nq, seed=143)
+    qv = oracle.vectorize(q["mz"], q["inten"], q["off"])
+    assign = oracle.ivf_assign(x, cent)
+    assert np.bincount(assign, minlength=nlist).max() > 12288
+    off, ids, vecs = oracle.build_lists(x, assign, nlist)
+    Dw, Iw = oracle.ivf_search(qv, cent, off, ids, vecs, nprobe, k)
+    engine.set_option("scan_engine", 0)
+    D, I = engine.ivf_search(CH, qv, k, nprobe)
+    assert np.array_equal(I, Iw)
+    assert np.array_equal(D, Dw)
+
+
 def test_near_ties_are_resolved_exactly(engine, oracle, synth):
     """Vectors that differ from each other by ~1 fp32 ulp of score: the fp16 scan cannot order
     them, the exact band re-rank must."""
