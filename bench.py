@@ -30,6 +30,9 @@ WORKLOADS = {
                label="C2: 16,384 queries vs 3M-vector library (2M targets + 1M decoys), charges 2-4"),
     "c2s": dict(n_targets=2_000_000, decoys=0.5, nq=16384, nlist=4096, nprobe=1024, k=1024, cpu_sample=128,
                 label="C2 (second point, nlist 4096)"),
+    # C5 point: 10 M vectors (mode B at N > 1: the `sharded` object; the library still fits one HBM, so mode A runs too)
+    "c5": dict(n_targets=6_666_667, decoys=0.5, nq=16384, nlist=16384, nprobe=1024, k=1024, cpu_sample=0,
+               label="C5 point: 16,384 queries vs 10M-vector library (6.67M targets + 3.33M decoys), charges 2-4"),
     "c1": dict(n_targets=200_000, decoys=0.5, nq=16384, nlist=256, nprobe=128, k=1024, cpu_sample=512,
                label="C1: 16,384 queries vs 200k+100k-decoy library, charges 2-4"),
     # streamed workloads (run_stream): the whole query set goes through the engine in batches of `nq`, like the
