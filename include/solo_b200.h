@@ -41,8 +41,13 @@ const char *solo_version(void);
 /* Run all work on an externally owned cudaStream_t (e.g. torch's current stream) so that
  * the caller's CUDA events bracket the kernels; NULL restores the handle's own stream. */
 int solo_set_stream(solo_handle *h, void *cuda_stream);
-/* Tuning/diagnostic switches. "scan_engine": 0 = tcgen05 tensor-core list scan with exact band
- * re-rank (default), 1 = exact CUDA-core list scan (same results; used to cross-check). */
+/* Tuning/diagnostic switches (results never depend on them). "scan_engine": 0 = tcgen05 tensor-core list scan with
+ * exact band re-rank (default), 1 = exact CUDA-core list scan (cross-check). "scan_ts": 0 (default) | 96 | 112 =
+ * swapped-operand scan with the list chunk in tensor memory, queries per tile. "round0_scores" (4096): size of the
+ * unconditional first scan round. "sort_items" (1): scan items ordered by cost. "compact_probes" (1): thresholded
+ * coarse pass. "train_balance" (0): balancing rounds of the k-means. "nvtx" (0): an NVTX range per stage.
+ * "scan_pairs", "scan_wide", "scan_hybrid", "round0_wide", "front_probes", "tc_nb", "tc_kbb", "tc_stages", "tc_debug":
+ * experiments documented in DESIGN.md section 4. */
 int solo_set_option(solo_handle *h, const char *key, int64_t value);
 /* Block until all work queued by this handle is complete. */
 int solo_synchronize(solo_handle *h);
