@@ -739,23 +739,27 @@ __global__ void round0_split_kernel(const int32_t *__restrict__ probes, int nq, 
     r0[q] = r;
 }
 
+// (lists without vectors on this GPU — mode B: lists another GPU owns — get no group: 7 of 8 probes at 8 GPUs)
 __global__ void group_count_kernel(const int32_t *__restrict__ probes, int nq, int nprobe,
-                                   const int32_t *__restrict__ r0, int nlist, int32_t *__restrict__ gcnt) {
+                                   const int32_t *__restrict__ r0, int nlist, const int64_t *__restrict__ list_off,
+                                   int32_t *__restrict__ gcnt) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nq * nprobe) return;
     int q = (int)(t / nprobe), j = (int)(t % nprobe);
     int l = probes[t];
+    if (list_off[l + 1] == list_off[l]) return;
     int round = j >= r0[q] ? 1 : 0;
     atomicAdd(&gcnt[round * nlist + l], 1);
 }
 
 __global__ void group_fill_kernel(const int32_t *__restrict__ probes, int nq, int nprobe,
                                   const int32_t *__restrict__ r0, int nlist, const int64_t *__restrict__ goff,
-                                  int32_t *__restrict__ gcur, int32_t *__restrict__ gq) {
+                                  const int64_t *__restrict__ list_off, int32_t *__restrict__ gcur, int32_t *__restrict__ gq) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nq * nprobe) return;
     int q = (int)(t / nprobe), j = (int)(t % nprobe);
     int l = probes[t];
+    if (list_off[l + 1] == list_off[l]) return;
     int round = j >= r0[q] ? 1 : 0;
     int pos = atomicAdd(&gcur[round * nlist + l], 1);
     gq[goff[round * nlist + l] + pos] = q;
@@ -1640,12 +1644,12 @@ void ivf_search(solo_handle *h, IvfIndex &ix, const IvfSearchArgs &a) {
                                                              r0.as<int32_t>());
         SOLO_CUDA(cudaMemsetAsync(gcnt.p, 0, (size_t)4 * nlist * sizeof(int32_t), st));
         group_count_kernel<<<div_up(npairs, 256), 256, 0, st>>>(d_probes, nq, nprobe, r0.as<int32_t>(), nlist,
-                                                                gcnt.as<int32_t>());
+                                                                ix.list_off.as<int64_t>(), gcnt.as<int32_t>());
         // one scan over [round0 lists | round1 lists]: goff[r*nlist + l]
         scan_counts_kernel<<<1, 1024, 0, st>>>(gcnt.as<int32_t>(), 2 * nlist, goff.as<int64_t>(), 0);
         group_fill_kernel<<<div_up(npairs, 256), 256, 0, st>>>(d_probes, nq, nprobe, r0.as<int32_t>(), nlist,
-                                                               goff.as<int64_t>(), gcnt.as<int32_t>() + 2 * nlist,
-                                                               gq.as<int32_t>());
+                                                               goff.as<int64_t>(), ix.list_off.as<int64_t>(),
+                                                               gcnt.as<int32_t>() + 2 * nlist, gq.as<int32_t>());
         SOLO_CUDA(cudaGetLastError());
     }
     SOLO_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * sizeof(int32_t), st));
